@@ -204,12 +204,12 @@ double gm_lgamma(double x) {
         if (x <= 0.9) {
             lg = -gm_log(x);
             if (x >= (Ymin - 1 + 0.27)) { y = 1 - x; i = 0; }
-            else if (x >= (Ymin - 1 - 0.27)) { y = x - (Tc - 1); i = 1; }
+            else if (x >= (Ymin - 1 - 0.23)) { y = x - (Tc - 1); i = 1; }
             else { y = x; i = 2; }
         } else {
             lg = 0;
             if (x >= (Ymin + 0.27)) { y = 2 - x; i = 0; }
-            else if (x >= (Ymin - 0.27)) { y = x - Tc; i = 1; }
+            else if (x >= (Ymin - 0.23)) { y = x - Tc; i = 1; }
             else { y = x - 1; i = 2; }
         }
         if (i == 0) {

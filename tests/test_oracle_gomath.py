@@ -43,7 +43,7 @@ def test_lgamma(orc):
     for x in np.concatenate([rng.uniform(0.01, 8, 3000), rng.uniform(8, 1e6, 1000)]):
         ref = float(special.gammaln(float(x)))
         got = L.gm_lgamma(float(x))
-        assert abs(got - ref) <= 4 * math.ulp(ref) + 1e-15, x
+        assert abs(got - ref) <= 4 * math.ulp(ref) + 4 * math.ulp(1.0), x  # absolute bound near the zeros at 1 and 2
 
 
 def test_round(orc):
