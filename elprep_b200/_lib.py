@@ -1,0 +1,86 @@
+"""ctypes binding of include/elprep_b200.h (libelprep_b200.so, built in-tree by __graft_entry__.build()).
+
+Fails loudly when the CUDA library is missing or no GPU is usable: there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "lib", "libelprep_b200.so")
+
+SO_KEEP, SO_UNKNOWN, SO_UNSORTED, SO_QUERYNAME, SO_COORDINATE = 0, 1, 2, 3, 4
+
+
+class ElpConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("n_contigs", C.c_int32), ("contig_names", C.POINTER(C.c_char_p)), ("contig_lengths", C.c_void_p),
+                ("n_read_groups", C.c_int32), ("rg_id", C.POINTER(C.c_char_p)), ("rg_lb", C.POINTER(C.c_char_p)), ("rg_pu", C.POINTER(C.c_char_p)),
+                ("max_cycle", C.c_int32), ("quantize_levels", C.c_int32), ("sqq", C.c_void_p), ("n_sqq", C.c_int32),
+                ("tablename_prefix", C.c_char_p), ("optical_pixel_distance", C.c_int32), ("profile", C.c_int32)]
+
+
+class ElpBatch(C.Structure):
+    _fields_ = [("n", C.c_uint64)] + [(k, C.c_void_p) for k in
+                ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "l_seq", "seq", "qual")]
+
+
+class ElpKernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint64), ("ms", C.c_double), ("alg_bytes", C.c_double)]
+
+
+EXPORTS = ["elp_create", "elp_destroy", "elp_last_error", "elp_reserve", "elp_reset", "elp_set_reference", "elp_set_known_sites",
+           "elp_append_batch", "elp_n_reads", "elp_sort_markdup", "elp_bqsr_gather", "elp_bqsr_tables_len", "elp_bqsr_n_cov",
+           "elp_bqsr_cov_name", "elp_bqsr_tables_get", "elp_bqsr_tables_put", "elp_bqsr_tables_device", "elp_bqsr_finalize",
+           "elp_bqsr_empirical_get", "elp_bqsr_apply", "elp_fetch", "elp_fetch_qual_bytes", "elp_debug_adapt", "elp_launch_count",
+           "elp_kernel_stats", "elp_synchronize", "elp_debug_sort_u64", "elp_debug_sort_u128"]
+
+_lib = None
+
+
+def load():
+    """Load the shared library (no GPU needed for loading; elp_create needs one)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(f"elprep_b200: CUDA library {SO_PATH} is missing -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
+                           "there is no CPU fallback")
+    L = C.CDLL(SO_PATH)
+    L.elp_last_error.restype = C.c_char_p
+    L.elp_last_error.argtypes = [C.c_void_p]
+    L.elp_create.argtypes = [C.POINTER(ElpConfig), C.POINTER(C.c_void_p)]
+    L.elp_destroy.argtypes = [C.c_void_p]
+    L.elp_destroy.restype = None
+    L.elp_n_reads.restype = C.c_uint64
+    L.elp_n_reads.argtypes = [C.c_void_p]
+    L.elp_bqsr_tables_len.restype = C.c_uint64
+    L.elp_bqsr_tables_len.argtypes = [C.c_void_p]
+    L.elp_bqsr_n_cov.argtypes = [C.c_void_p]
+    L.elp_bqsr_cov_name.restype = C.c_char_p
+    L.elp_bqsr_cov_name.argtypes = [C.c_void_p, C.c_int32]
+    L.elp_launch_count.restype = C.c_uint64
+    L.elp_launch_count.argtypes = [C.c_void_p]
+    L.elp_fetch_qual_bytes.restype = C.c_uint64
+    L.elp_fetch_qual_bytes.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    L.elp_reserve.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]
+    L.elp_reset.argtypes = [C.c_void_p]
+    L.elp_set_reference.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64]
+    L.elp_set_known_sites.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_int]
+    L.elp_append_batch.argtypes = [C.c_void_p, C.POINTER(ElpBatch)]
+    L.elp_sort_markdup.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.elp_bqsr_gather.argtypes = [C.c_void_p]
+    L.elp_bqsr_tables_get.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.elp_bqsr_tables_put.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.elp_bqsr_tables_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.elp_bqsr_finalize.argtypes = [C.c_void_p, C.c_char_p]
+    L.elp_bqsr_empirical_get.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.elp_bqsr_apply.argtypes = [C.c_void_p]
+    L.elp_fetch.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.elp_debug_adapt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.elp_kernel_stats.argtypes = [C.c_void_p, C.POINTER(ElpKernelStat), C.c_int]
+    L.elp_synchronize.argtypes = [C.c_void_p]
+    L.elp_debug_sort_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    L.elp_debug_sort_u128.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    _lib = L
+    return L

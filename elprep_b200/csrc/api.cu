@@ -1,0 +1,404 @@
+// api.cu -- the C ABI of include/elprep_b200.h: context lifecycle, batch ingest, phase entry points, fetch.
+#include <algorithm>
+#include <map>
+#include "../../include/elprep_b200.h"
+#include "ctx.h"
+
+int run_apply_kernel(elp_ctx* c, bool with_lut);
+
+namespace {
+
+thread_local std::string g_create_error;
+
+inline unsigned nblk(uint64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+__global__ void __launch_bounds__(256) rebase_kernel(uint64_t n, const uint64_t* __restrict__ rel, uint64_t base, uint64_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rel[i] + base;
+}
+__global__ void __launch_bounds__(256) lens_kernel(uint64_t n, const int32_t* __restrict__ lseq, uint32_t* __restrict__ qlen, uint32_t* __restrict__ slen) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const uint32_t l = (uint32_t)lseq[i]; qlen[i] = l; slen[i] = (l + 1) >> 1; }
+}
+__global__ void __launch_bounds__(256) add_base_kernel(uint64_t n, uint64_t* __restrict__ v, uint64_t base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += base;
+}
+__global__ void __launch_bounds__(256) widen_kernel(uint64_t n, const uint32_t* __restrict__ in, uint64_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void __launch_bounds__(256) rel_off_kernel(uint64_t n, const uint64_t* __restrict__ off, uint64_t first, uint64_t* __restrict__ out) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = off[first + i] - off[first];
+}
+
+template <class T> int grow(elp_ctx* c, DBuf<T>& b, size_t need, size_t keep) {
+    cudaError_t e = b.reserve(need, c->stream, keep);
+    if (e != cudaSuccess) return c->fail(e == cudaErrorMemoryAllocation ? E_NOMEM : E_CUDA, "device allocation of %zu bytes failed: %s", need * sizeof(T), cudaGetErrorString(e));
+    return E_OK;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+}  // namespace
+
+int upload_side_inputs(elp_ctx* c) {
+    if (!c->side_dirty) return E_OK;
+    const int nc = c->n_contigs;
+    std::vector<const uint8_t*> rp(nc); std::vector<const int32_t*> sp(nc);
+    for (int i = 0; i < nc; i++) { rp[i] = c->d_ref[i]; sp[i] = c->d_sites[i]; }
+    if (nc) {
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_ref_ptrs, rp.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_ref_len, c->ref_len.data(), nc * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_site_ptrs, sp.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_n_sites, c->n_sites.data(), nc * 8, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    }
+    c->side_dirty = false;
+    return E_OK;
+}
+
+extern "C" {
+
+const char* elp_last_error(const elp_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int elp_create(const elp_config* cfg, elp_ctx** out) {
+    if (!cfg || !out) { g_create_error = "elp_create: null argument"; return ELP_EINVAL; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || cfg->device < 0 || cfg->device >= ndev) {
+        g_create_error = std::string("elp_create: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device ordinal out of range") + "); this library has no CPU fallback";
+        return ELP_ENODEVICE;
+    }
+    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess) { g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e); return ELP_ENODEVICE; }
+    elp_ctx* c = new elp_ctx();
+    c->device = cfg->device;
+    c->profile = cfg->profile != 0;
+    auto bail = [&](int code) { g_create_error = c->err; elp_destroy(c); return code; };
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { c->err = "cudaStreamCreate failed"; return bail(ELP_ECUDA); }
+    c->n_contigs = cfg->n_contigs;
+    for (int i = 0; i < cfg->n_contigs; i++) { c->contig_len.push_back(cfg->contig_lengths[i]); c->contig_names.push_back(cfg->contig_names && cfg->contig_names[i] ? cfg->contig_names[i] : ""); }
+    // library ids: equal LB strings share an id (lbTable, mark-duplicates.go:413-423); covariates: PU if present else ID (bqsr.go:35-51)
+    c->n_rg = cfg->n_read_groups;
+    std::map<std::string, int> libs, covs;
+    for (int i = 0; i < c->n_rg; i++) {
+        if (!cfg->rg_id || !cfg->rg_id[i]) { c->err = "Missing mandatory ID entry in an @RG line in a SAM file header."; return bail(ELP_EINVAL); }
+        const char* lb = cfg->rg_lb ? cfg->rg_lb[i] : nullptr;
+        if (lb) { auto it = libs.find(lb); if (it == libs.end()) it = libs.emplace(lb, (int)libs.size()).first; c->rg_lib.push_back(it->second); } else c->rg_lib.push_back(-1);
+        const char* pu = cfg->rg_pu ? cfg->rg_pu[i] : nullptr;
+        std::string name = pu ? pu : cfg->rg_id[i];
+        auto it = covs.find(name);
+        if (it == covs.end()) { it = covs.emplace(name, (int)c->cov_names.size()).first; c->cov_names.push_back(name); }
+        c->rg_cov.push_back(it->second);
+    }
+    c->n_lib = (int)libs.size();
+    c->max_cycle = cfg->max_cycle > 0 ? cfg->max_cycle : 500;
+    c->quantize_levels = cfg->quantize_levels;
+    if (cfg->sqq && cfg->n_sqq > 0) c->sqq.assign(cfg->sqq, cfg->sqq + cfg->n_sqq);
+    if (cfg->tablename_prefix) c->prefix = cfg->tablename_prefix;
+    c->optical_pixel_distance = cfg->optical_pixel_distance > 0 ? cfg->optical_pixel_distance : 100;
+    c->geom.n_cov = (int)c->cov_names.size(); c->geom.max_cycle = c->max_cycle;
+    const int nc = std::max(1, c->n_contigs), nr = std::max(1, c->n_rg);
+    bool ok = cudaMalloc(&c->d_rg_lib, nr * 4) == cudaSuccess && cudaMalloc(&c->d_rg_cov, nr * 4) == cudaSuccess && cudaMalloc(&c->d_contig_len, nc * 4) == cudaSuccess &&
+              cudaMalloc(&c->d_ranges, sizeof(DeviceRanges)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess &&
+              cudaMalloc(&c->d_ref_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_ref_len, nc * 8) == cudaSuccess &&
+              cudaMalloc(&c->d_site_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_n_sites, nc * 8) == cudaSuccess &&
+              cudaMalloc(&c->d_tables, std::max<size_t>(16, c->geom.cells() * 2 * sizeof(int64_t))) == cudaSuccess;
+    if (!ok) { c->err = "device allocation failed in elp_create"; return bail(ELP_ENOMEM); }
+    if (c->n_rg) { cudaMemcpy(c->d_rg_lib, c->rg_lib.data(), c->n_rg * 4, cudaMemcpyHostToDevice); cudaMemcpy(c->d_rg_cov, c->rg_cov.data(), c->n_rg * 4, cudaMemcpyHostToDevice); }
+    if (c->n_contigs) cudaMemcpy(c->d_contig_len, c->contig_len.data(), c->n_contigs * 4, cudaMemcpyHostToDevice);
+    cudaMemset(c->d_err, 0, 4);
+    cudaMemset(c->d_tables, 0, std::max<size_t>(16, c->geom.cells() * 2 * sizeof(int64_t)));
+    c->d_ref.assign(c->n_contigs, nullptr); c->ref_len.assign(c->n_contigs, 0);
+    c->d_sites.assign(c->n_contigs, nullptr); c->n_sites.assign(c->n_contigs, 0);
+    if ((e = cudaGetLastError()) != cudaSuccess) { c->err = std::string("elp_create: ") + cudaGetErrorString(e); return bail(ELP_ECUDA); }
+    *out = c;
+    return ELP_OK;
+}
+
+void elp_destroy(elp_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto p : c->d_ref) if (p) cudaFree(p);
+    for (auto p : c->d_sites) if (p) cudaFree(p);
+    void* singles[] = {c->d_rg_lib, c->d_rg_cov, c->d_contig_len, c->d_ranges, c->d_err, (void*)c->d_ref_ptrs, c->d_ref_len, (void*)c->d_site_ptrs, c->d_n_sites, c->d_tables,
+                       c->d_lut, c->d_cov_exists, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
+    for (void* p : singles) if (p) cudaFree(p);
+    c->refid.release(); c->pos.release(); c->nref.release(); c->pnext.release(); c->tlen.release(); c->rg.release(); c->flag.release(); c->mapq.release();
+    c->qname_off.release(); c->cigar_off.release(); c->qual_off.release(); c->seq_off.release(); c->qname.release(); c->seq.release(); c->qual.release(); c->cigar.release();
+    c->lseq_stage.release(); c->off_stage.release(); c->upos.release(); c->score.release(); c->qhash.release(); c->keys_a.release(); c->keys_b.release();
+    c->vals_a.release(); c->vals_b.release(); c->mate.release(); c->pair_a.release(); c->pair_b.release(); c->scan_tmp.release(); c->scan_blk.release(); c->bytes_tmp.release();
+    c->perm.release(); c->s_refid.release(); c->s_pos.release(); c->s_nref.release(); c->s_pnext.release(); c->s_tlen.release(); c->s_rg.release(); c->s_lseq.release();
+    c->s_flag.release(); c->s_mapq.release(); c->s_qual_off.release(); c->s_seq_off.release(); c->s_cigar_off.release(); c->s_out_off.release(); c->s_ncigar.release(); c->qual_out.release();
+    for (auto& pe : c->pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int elp_reset(elp_ctx* c) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->n = c->n_qname = c->n_cigar = c->n_qual = c->n_seq = 0;
+    c->adapted = c->sorted = c->qual_out_valid = c->gathered = c->finalized = false;
+    c->launches = 0;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_err, 0, 4, c->stream));
+    return ELP_OK;
+}
+
+int elp_reserve(elp_ctx* c, uint64_t n_reads, uint64_t n_bases, uint64_t n_cigar_ops, uint64_t n_qname_bytes) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    std::lock_guard<std::mutex> lk(c->append_mu);
+    const size_t n = n_reads + 1;
+    TRY(grow(c, c->refid, n, c->n)); TRY(grow(c, c->pos, n, c->n)); TRY(grow(c, c->nref, n, c->n)); TRY(grow(c, c->pnext, n, c->n)); TRY(grow(c, c->tlen, n, c->n));
+    TRY(grow(c, c->rg, n, c->n)); TRY(grow(c, c->flag, n + 1, c->n)); TRY(grow(c, c->mapq, n, c->n));
+    TRY(grow(c, c->qname_off, n + 1, c->n + 1)); TRY(grow(c, c->cigar_off, n + 1, c->n + 1)); TRY(grow(c, c->qual_off, n + 1, c->n + 1)); TRY(grow(c, c->seq_off, n + 1, c->n + 1));
+    TRY(grow(c, c->qname, n_qname_bytes + 64, c->n_qname)); TRY(grow(c, c->cigar, n_cigar_ops + 16, c->n_cigar));
+    TRY(grow(c, c->qual, n_bases + 64, c->n_qual)); TRY(grow(c, c->seq, n_bases / 2 + n_reads + 64, c->n_seq));
+    return ELP_OK;
+}
+
+int elp_set_reference(elp_ctx* c, int32_t contig, const uint8_t* bases, uint64_t n) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (contig < 0 || contig >= c->n_contigs) return c->fail(E_INVAL, "elp_set_reference: contig %d out of range", contig);
+    if (c->d_ref[contig]) { cudaFree(c->d_ref[contig]); c->d_ref[contig] = nullptr; }
+    CUDA_TRY(c, cudaMalloc(&c->d_ref[contig], n + 16));
+    CUDA_TRY(c, cudaMemcpy(c->d_ref[contig], bases, n, cudaMemcpyHostToDevice));
+    c->ref_len[contig] = n; c->side_dirty = true;
+    return ELP_OK;
+}
+
+int elp_set_known_sites(elp_ctx* c, int32_t contig, const int32_t* se, uint64_t n_intervals, int already_flat) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (contig < 0 || contig >= c->n_contigs) return c->fail(E_INVAL, "elp_set_known_sites: contig %d out of range", contig);
+    std::vector<int32_t> v(se, se + 2 * n_intervals);
+    uint64_t n = n_intervals;
+    if (!already_flat && n > 1) {
+        // stable sort by start (intervals.ParallelSortByStart) then Flatten (intervals/intervals.go:88-117): merge while next.Start <= cur.End
+        std::vector<std::pair<int32_t, int32_t>> iv(n);
+        for (uint64_t i = 0; i < n; i++) iv[i] = {v[2 * i], v[2 * i + 1]};
+        std::stable_sort(iv.begin(), iv.end(), [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first < b.first; });
+        uint64_t m = 0;
+        for (uint64_t i = 0; i < n; i++) {
+            if (m > 0 && iv[i].first <= iv[m - 1].second) { if (iv[i].second > iv[m - 1].second) iv[m - 1].second = iv[i].second; }
+            else iv[m++] = iv[i];
+        }
+        n = m;
+        for (uint64_t i = 0; i < n; i++) { v[2 * i] = iv[i].first; v[2 * i + 1] = iv[i].second; }
+    }
+    if (c->d_sites[contig]) { cudaFree(c->d_sites[contig]); c->d_sites[contig] = nullptr; }
+    if (n) {
+        CUDA_TRY(c, cudaMalloc(&c->d_sites[contig], n * 8));
+        CUDA_TRY(c, cudaMemcpy(c->d_sites[contig], v.data(), n * 8, cudaMemcpyHostToDevice));
+    }
+    c->n_sites[contig] = n; c->side_dirty = true;
+    return ELP_OK;
+}
+
+uint64_t elp_n_reads(const elp_ctx* c) { return c ? c->n : 0; }
+
+int elp_append_batch(elp_ctx* c, const elp_batch* b) {
+    if (!c || !b) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    std::lock_guard<std::mutex> lk(c->append_mu);
+    const uint64_t bn = b->n;
+    if (bn == 0) return ELP_OK;
+    if (c->sorted) return c->fail(E_STATE, "elp_append_batch after elp_sort_markdup (call elp_reset first)");
+    const uint64_t n0 = c->n, n1 = n0 + bn;
+    if (n1 >= (1ull << 32)) return c->fail(E_LIMIT, "more than 2^32-1 reads in one context");
+    const uint64_t bq = b->qname_off[bn] - b->qname_off[0], bc = b->cigar_off[bn] - b->cigar_off[0];
+    uint64_t bbases = 0, bseq = 0;
+    for (uint64_t i = 0; i < bn; i++) { const uint64_t l = (uint64_t)(uint32_t)b->l_seq[i]; bbases += l; bseq += (l + 1) >> 1; }
+    TRY(grow(c, c->refid, n1 + 1, n0)); TRY(grow(c, c->pos, n1 + 1, n0)); TRY(grow(c, c->nref, n1 + 1, n0)); TRY(grow(c, c->pnext, n1 + 1, n0)); TRY(grow(c, c->tlen, n1 + 1, n0));
+    TRY(grow(c, c->rg, n1 + 1, n0)); TRY(grow(c, c->flag, n1 + 2, n0)); TRY(grow(c, c->mapq, n1 + 1, n0));
+    TRY(grow(c, c->qname_off, n1 + 2, n0 + 1)); TRY(grow(c, c->cigar_off, n1 + 2, n0 + 1)); TRY(grow(c, c->qual_off, n1 + 2, n0 + 1)); TRY(grow(c, c->seq_off, n1 + 2, n0 + 1));
+    TRY(grow(c, c->qname, c->n_qname + bq + 64, c->n_qname)); TRY(grow(c, c->cigar, c->n_cigar + bc + 16, c->n_cigar));
+    TRY(grow(c, c->qual, c->n_qual + bbases + 64, c->n_qual)); TRY(grow(c, c->seq, c->n_seq + bseq + 64, c->n_seq));
+    TRY(grow(c, c->off_stage, bn + 2, 0)); TRY(grow(c, c->lseq_stage, bn + 2, 0)); TRY(grow(c, c->scan_tmp, 2 * bn + 8, 0));
+    cudaStream_t s = c->stream;
+    const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
+    CUDA_TRY(c, cudaMemcpyAsync(c->refid.p + n0, b->refid, bn * 4, H2D, s)); CUDA_TRY(c, cudaMemcpyAsync(c->pos.p + n0, b->pos, bn * 4, H2D, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->nref.p + n0, b->nref, bn * 4, H2D, s)); CUDA_TRY(c, cudaMemcpyAsync(c->pnext.p + n0, b->pnext, bn * 4, H2D, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tlen.p + n0, b->tlen, bn * 4, H2D, s)); CUDA_TRY(c, cudaMemcpyAsync(c->rg.p + n0, b->rg, bn * 4, H2D, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->flag.p + n0, b->flag, bn * 2, H2D, s)); CUDA_TRY(c, cudaMemcpyAsync(c->mapq.p + n0, b->mapq, bn, H2D, s));
+    if (bq) CUDA_TRY(c, cudaMemcpyAsync(c->qname.p + c->n_qname, b->qname + b->qname_off[0], bq, H2D, s));
+    if (bc) CUDA_TRY(c, cudaMemcpyAsync(c->cigar.p + c->n_cigar, b->cigar + b->cigar_off[0], bc * 4, H2D, s));
+    if (bbases) CUDA_TRY(c, cudaMemcpyAsync(c->qual.p + c->n_qual, b->qual, bbases, H2D, s));
+    if (bseq) CUDA_TRY(c, cudaMemcpyAsync(c->seq.p + c->n_seq, b->seq, bseq, H2D, s));
+    // offsets: batch-relative -> arena-global
+    CUDA_TRY(c, cudaMemcpyAsync(c->off_stage.p, b->qname_off, (bn + 1) * 8, H2D, s));
+    rebase_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->off_stage.p, c->n_qname - b->qname_off[0], c->qname_off.p + n0); c->launches++;
+    CUDA_TRY(c, cudaStreamSynchronize(s));   // off_stage is reused below
+    CUDA_TRY(c, cudaMemcpyAsync(c->off_stage.p, b->cigar_off, (bn + 1) * 8, H2D, s));
+    rebase_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->off_stage.p, c->n_cigar - b->cigar_off[0], c->cigar_off.p + n0); c->launches++;
+    CUDA_TRY(c, cudaMemcpyAsync(c->lseq_stage.p, b->l_seq, bn * 4, H2D, s));
+    uint32_t* qlen = c->scan_tmp.p; uint32_t* slen = c->scan_tmp.p + bn + 4;
+    lens_kernel<<<nblk(bn, 256), 256, 0, s>>>(bn, c->lseq_stage.p, qlen, slen); c->launches++;
+    LAUNCH_CHECK(c);
+    TRY(exclusive_scan_u32_to_u64(c, qlen, c->qual_off.p + n0, bn));
+    if (c->n_qual) { add_base_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->qual_off.p + n0, c->n_qual); c->launches++; }
+    TRY(exclusive_scan_u32_to_u64(c, slen, c->seq_off.p + n0, bn));
+    if (c->n_seq) { add_base_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->seq_off.p + n0, c->n_seq); c->launches++; }
+    LAUNCH_CHECK(c);
+    CUDA_TRY(c, cudaStreamSynchronize(s));   // the caller's buffers may be released after return (cgo pointer rules)
+    c->n = n1; c->n_qname += bq; c->n_cigar += bc; c->n_qual += bbases; c->n_seq += bseq;
+    c->adapted = false;
+    return ELP_OK;
+}
+
+int elp_sort_markdup(elp_ctx* c, int sorting_order, int mark_duplicates) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (c->sorted) return c->fail(E_STATE, "elp_sort_markdup called twice (call elp_reset first)");
+    if (sorting_order == ELP_SO_QUERYNAME) return c->fail(E_INVAL, "queryname order is not on the device path");
+    if (mark_duplicates) TRY(phase_markdup(c));
+    TRY(phase_coordinate_sort(c, sorting_order == ELP_SO_COORDINATE));
+    return ELP_OK;
+}
+
+int elp_bqsr_gather(elp_ctx* c) { if (!c) return ELP_EINVAL; cudaSetDevice(c->device); return phase_bqsr_gather(c); }
+int elp_bqsr_finalize(elp_ctx* c, const char* report_path) { if (!c) return ELP_EINVAL; cudaSetDevice(c->device); return phase_bqsr_finalize(c, report_path); }
+int elp_bqsr_apply(elp_ctx* c) { if (!c) return ELP_EINVAL; cudaSetDevice(c->device); return phase_bqsr_apply(c); }
+
+uint64_t elp_bqsr_tables_len(const elp_ctx* c) { return c ? (uint64_t)c->geom.cells() * 2 : 0; }
+int32_t elp_bqsr_n_cov(const elp_ctx* c) { return c ? c->geom.n_cov : 0; }
+const char* elp_bqsr_cov_name(const elp_ctx* c, int32_t cov) { return (c && cov >= 0 && cov < (int)c->cov_names.size()) ? c->cov_names[cov].c_str() : nullptr; }
+int elp_bqsr_tables_get(elp_ctx* c, int64_t* dense, uint64_t n) {
+    if (!c || !dense) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (n != elp_bqsr_tables_len(c)) return c->fail(E_INVAL, "elp_bqsr_tables_get: expected %llu values", (unsigned long long)elp_bqsr_tables_len(c));
+    CUDA_TRY(c, cudaMemcpyAsync(dense, c->d_tables, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ELP_OK;
+}
+int elp_bqsr_tables_put(elp_ctx* c, const int64_t* dense, uint64_t n) {
+    if (!c || !dense) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (n != elp_bqsr_tables_len(c)) return c->fail(E_INVAL, "elp_bqsr_tables_put: expected %llu values", (unsigned long long)elp_bqsr_tables_len(c));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_tables, dense, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->gathered = true; c->finalized = false;
+    return ELP_OK;
+}
+int elp_bqsr_tables_device(elp_ctx* c, void** p, uint64_t* n) {
+    if (!c || !p || !n) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    *p = c->d_tables; *n = elp_bqsr_tables_len(c);
+    c->finalized = false;
+    return ELP_OK;
+}
+int elp_bqsr_empirical_get(elp_ctx* c, uint8_t* emp, uint64_t n) {
+    if (!c || !emp) return ELP_EINVAL;
+    if (!c->finalized) return c->fail(E_STATE, "elp_bqsr_empirical_get before elp_bqsr_finalize");
+    if (n != c->geom.cells()) return c->fail(E_INVAL, "elp_bqsr_empirical_get: expected %zu values", c->geom.cells());
+    std::copy(c->h_emp.begin(), c->h_emp.end(), emp);
+    return ELP_OK;
+}
+
+uint64_t elp_fetch_qual_bytes(elp_ctx* c, uint64_t first, uint64_t n) {
+    if (!c || !c->sorted || first + n > c->n) return 0;
+    cudaSetDevice(c->device);
+    uint64_t v[2] = {0, 0};
+    cudaMemcpyAsync(&v[0], c->s_out_off.p + first, 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaMemcpyAsync(&v[1], c->s_out_off.p + first + n, 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaStreamSynchronize(c->stream);
+    return v[1] - v[0];
+}
+
+int elp_fetch(elp_ctx* c, uint64_t first, uint64_t n, uint64_t* record_index, uint16_t* flag, uint64_t* qual_off, uint8_t* qual, uint64_t qual_capacity) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (!c->sorted) return c->fail(E_STATE, "elp_fetch before elp_sort_markdup");
+    if (first + n > c->n) return c->fail(E_INVAL, "elp_fetch: range [%llu,%llu) exceeds %llu reads", (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)c->n);
+    if (n == 0) { if (qual_off) qual_off[0] = 0; return ELP_OK; }
+    cudaStream_t s = c->stream;
+    if (record_index) {
+        TRY(grow(c, c->off_stage, n + 2, 0));
+        widen_kernel<<<nblk(n, 256), 256, 0, s>>>(n, c->perm.p + first, c->off_stage.p); c->launches++;
+        CUDA_TRY(c, cudaMemcpyAsync(record_index, c->off_stage.p, n * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+    }
+    if (flag) CUDA_TRY(c, cudaMemcpyAsync(flag, c->s_flag.p + first, n * 2, cudaMemcpyDeviceToHost, s));
+    if (qual_off) {
+        TRY(grow(c, c->off_stage, n + 2, 0));
+        rel_off_kernel<<<nblk(n + 1, 256), 256, 0, s>>>(n, c->s_out_off.p, first, c->off_stage.p); c->launches++;
+        CUDA_TRY(c, cudaMemcpyAsync(qual_off, c->off_stage.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (qual) {
+        if (!c->qual_out_valid) TRY(run_apply_kernel(c, false));   // no BQSR: just the QUAL bytes in output order
+        uint64_t v[2];
+        CUDA_TRY(c, cudaMemcpyAsync(&v[0], c->s_out_off.p + first, 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaMemcpyAsync(&v[1], c->s_out_off.p + first + n, 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (v[1] - v[0] > qual_capacity) return c->fail(E_INVAL, "elp_fetch: qual buffer too small (%llu > %llu)", (unsigned long long)(v[1] - v[0]), (unsigned long long)qual_capacity);
+        CUDA_TRY(c, cudaMemcpyAsync(qual, c->qual_out.p + v[0], v[1] - v[0], cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(s));
+    return ELP_OK;
+}
+
+int elp_debug_adapt(elp_ctx* c, int32_t* upos, int32_t* score) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    TRY(phase_adapt(c));
+    if (upos) CUDA_TRY(c, cudaMemcpyAsync(upos, c->upos.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (score) CUDA_TRY(c, cudaMemcpyAsync(score, c->score.p, c->n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ELP_OK;
+}
+
+uint64_t elp_launch_count(const elp_ctx* c) { return c ? c->launches : 0; }
+int elp_synchronize(elp_ctx* c) { if (!c) return ELP_EINVAL; cudaSetDevice(c->device); CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return ELP_OK; }
+int elp_kernel_stats(elp_ctx* c, elp_kernel_stat* out, int cap) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    c->resolve_events();
+    int k = 0;
+    for (auto& kv : c->stats) {
+        if (k >= cap) break;
+        std::snprintf(out[k].name, sizeof out[k].name, "%s", kv.first.c_str());
+        out[k].launches = kv.second.launches; out[k].ms = kv.second.ms; out[k].alg_bytes = kv.second.alg_bytes;
+        k++;
+    }
+    return k;
+}
+
+int elp_debug_sort_u64(elp_ctx* c, uint64_t* keys, uint32_t* vals, uint64_t n, int key_bits) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    TRY(grow(c, c->keys_a, n + 4, 0)); TRY(grow(c, c->keys_b, n + 4, 0)); TRY(grow(c, c->vals_a, n + 4, 0)); TRY(grow(c, c->vals_b, n + 4, 0));
+    CUDA_TRY(c, cudaMemcpyAsync(c->keys_a.p, keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->vals_a.p, vals, n * 4, cudaMemcpyHostToDevice, c->stream));
+    bool in_b = false;
+    TRY(radix_sort_u64(c, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, key_bits, &in_b, "u64"));
+    CUDA_TRY(c, cudaMemcpyAsync(keys, in_b ? c->keys_b.p : c->keys_a.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(vals, in_b ? c->vals_b.p : c->vals_a.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return ELP_OK;
+}
+
+int elp_debug_sort_u128(elp_ctx* c, uint64_t* keys_hi, uint64_t* keys_lo, uint32_t* vals, uint64_t n, int key_bits) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    TRY(grow(c, c->keys_a, 2 * n + 4, 0)); TRY(grow(c, c->keys_b, 2 * n + 4, 0)); TRY(grow(c, c->vals_a, n + 4, 0)); TRY(grow(c, c->vals_b, n + 4, 0));
+    std::vector<uint64_t> inter(2 * n);
+    for (uint64_t i = 0; i < n; i++) { inter[2 * i] = keys_lo[i]; inter[2 * i + 1] = keys_hi[i]; }
+    CUDA_TRY(c, cudaMemcpyAsync(c->keys_a.p, inter.data(), n * 16, cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(c->vals_a.p, vals, n * 4, cudaMemcpyHostToDevice, c->stream));
+    bool in_b = false;
+    TRY(radix_sort_u128(c, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, key_bits, &in_b, "u128"));
+    CUDA_TRY(c, cudaMemcpyAsync(inter.data(), in_b ? c->keys_b.p : c->keys_a.p, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(vals, in_b ? c->vals_b.p : c->vals_a.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (uint64_t i = 0; i < n; i++) { keys_lo[i] = inter[2 * i]; keys_hi[i] = inter[2 * i + 1]; }
+    return ELP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,238 @@
+// radix_sort.cuh -- hand-written onesweep LSD radix sort for sm_100a (keys u64 or u128, u32 payload).
+//
+// Replaces pargo sort.StableSort as used by By(CoordinateLess).ParallelStableSort (sam/sam-types.go:599-641)
+// and the sharded-map grouping of filters/mark-duplicates.go:210-396 (sort-by-key + segmented scan instead of
+// LoadOrStore).  Stable, so equal keys keep arrival order exactly as the reference's stable merge sort does.
+//
+// Structure (one read of the keys for all digit histograms, then ONE read + ONE write of keys and payload per
+// digit pass -- algorithmic bytes N*(K + 2*P*(K+V))):
+//   rs_hist_kernel      all P digit histograms in a single pass over the keys (shared-memory counters)
+//   rs_scan_kernel      exclusive scan of each 256-bin histogram -> global digit offsets
+//   rs_onesweep_kernel  per pass: warp-striped coalesced key loads, per-warp ranking with match.any,
+//                       chained-scan (decoupled look-back) across tiles for the global digit offsets, tile-local
+//                       reorder through shared memory so the scatter leaves in digit-contiguous runs.
+// Keys are compacted by the caller so that only `key_bits` low bits are significant; P = ceil(key_bits/8)
+// passes with balanced digit widths <= 8.
+#pragma once
+#include "common.cuh"
+
+namespace rs {
+
+constexpr int RADIX = 256;
+constexpr int MAX_PASSES = 16;
+constexpr uint32_t ST_PARTIAL = 1u << 30, ST_INCLUSIVE = 2u << 30, ST_VALMASK = (1u << 30) - 1;
+
+struct Plan {
+    int n_passes;
+    int shift[MAX_PASSES];
+    int bits[MAX_PASSES];
+};
+
+inline Plan make_plan(int key_bits) {
+    Plan p{};
+    if (key_bits < 1) key_bits = 1;
+    p.n_passes = (key_bits + 7) / 8;
+    int base = key_bits / p.n_passes, extra = key_bits % p.n_passes, s = 0;
+    for (int i = 0; i < p.n_passes; i++) {
+        p.bits[i] = base + (i < extra ? 1 : 0);
+        p.shift[i] = s;
+        s += p.bits[i];
+    }
+    return p;
+}
+
+struct K64 {
+    uint64_t v;
+    __device__ __forceinline__ static K64 load(const K64* p) { K64 k; k.v = ld_stream_u64(reinterpret_cast<const uint64_t*>(p)); return k; }
+    __device__ __forceinline__ uint32_t digit(int shift, uint32_t mask) const { return (uint32_t)(v >> shift) & mask; }
+};
+struct __align__(16) K128 {
+    uint64_t lo, hi;
+    __device__ __forceinline__ static K128 load(const K128* p) { uint4 r = ld_stream_u4(p); K128 k; k.lo = (uint64_t)r.x | ((uint64_t)r.y << 32); k.hi = (uint64_t)r.z | ((uint64_t)r.w << 32); return k; }
+    __device__ __forceinline__ uint32_t digit(int shift, uint32_t mask) const {
+        uint64_t w = shift >= 64 ? (hi >> (shift - 64)) : (shift == 0 ? lo : ((lo >> shift) | (hi << (64 - shift))));
+        return (uint32_t)w & mask;
+    }
+};
+
+// ---------------------------------------------------------------- all digit histograms in one pass
+template <class K>
+__global__ void __launch_bounds__(512) rs_hist_kernel(const K* __restrict__ keys, uint64_t n, Plan plan, uint32_t* __restrict__ ghist) {
+    __shared__ uint32_t sh[MAX_PASSES * RADIX];
+    for (int i = threadIdx.x; i < plan.n_passes * RADIX; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const unsigned lane = lane_id();
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; (i - lane) < n; i += stride) {
+        bool valid = i < n;
+        K k{};
+        if (valid) k = K::load(keys + i);
+        unsigned vmask = __ballot_sync(FULL_MASK, valid);
+#pragma unroll 1
+        for (int p = 0; p < plan.n_passes; p++) {
+            uint32_t d = valid ? k.digit(plan.shift[p], (1u << plan.bits[p]) - 1) : 0xffffffffu;
+            // sorted / low-entropy inputs: the whole warp hits one bin -> one add instead of a 32-way same-address conflict
+            uint32_t d0 = __shfl_sync(FULL_MASK, d, __ffs(vmask) - 1);
+            bool uni = __all_sync(FULL_MASK, !valid || d == d0);
+            if (uni) { if (lane == (unsigned)(__ffs(vmask) - 1)) atomicAdd(&sh[p * RADIX + d0], __popc(vmask)); }
+            else if (valid) atomicAdd(&sh[p * RADIX + d], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.n_passes * RADIX; i += blockDim.x) { uint32_t c = sh[i]; if (c) atomicAdd(&ghist[i], c); }
+}
+
+// exclusive scan of each pass' 256-bin histogram (one block per pass)
+static __global__ void rs_scan_kernel(const uint32_t* __restrict__ ghist, uint32_t* __restrict__ gofs) {
+    __shared__ uint32_t wsum[8];
+    const int p = blockIdx.x, d = threadIdx.x;
+    uint32_t c = ghist[p * RADIX + d], x = c;
+    const unsigned lane = d & 31, w = d >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= (unsigned)o) x += y; }
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t add = 0;
+    for (unsigned i = 0; i < w; i++) add += wsum[i];
+    gofs[p * RADIX + d] = x - c + add;
+}
+
+// ---------------------------------------------------------------- one digit pass
+template <class K, int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
+                                                              const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
+                                                              uint64_t n, int shift, int bits, const uint32_t* __restrict__ gofs,
+                                                              uint32_t* __restrict__ status, uint32_t* __restrict__ tile_counter) {
+    constexpr int WARPS = THREADS / 32, TILE = THREADS * ITEMS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* warp_hist = reinterpret_cast<uint32_t*>(smem_raw);                // [WARPS][RADIX]
+    K* sk = reinterpret_cast<K*>(smem_raw + (size_t)WARPS * RADIX * 4);         // [TILE]; reused for the payload
+    uint32_t* sv = reinterpret_cast<uint32_t*>(sk);
+    __shared__ uint32_t s_tile, digit_start[RADIX], gbase[RADIX], wsum[8];
+
+    const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t mask = (1u << bits) - 1;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);   // ticket: a tile only ever waits on tiles that already started
+    for (int i = tid; i < WARPS * RADIX; i += THREADS) warp_hist[i] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint64_t base = (uint64_t)tile * TILE;
+    const uint32_t n_valid = (uint32_t)((n - base) < (uint64_t)TILE ? (n - base) : (uint64_t)TILE);
+
+    // warp-striped loads: element (warp, j, lane) <-> tile index warp*ITEMS*32 + j*32 + lane (stable order = that index)
+    K key[ITEMS];
+    uint32_t val[ITEMS], rank[ITEMS];
+    const uint32_t wbase = warp * ITEMS * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        uint32_t t = wbase + j * 32;
+        if (t < n_valid) { key[j] = K::load(keys_in + base + t); val[j] = ld_stream_u32(vals_in + base + t); }
+    }
+    uint32_t* wh = warp_hist + warp * RADIX;
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        const bool valid = (wbase + j * 32) < n_valid;
+        const uint32_t d = valid ? key[j].digit(shift, mask) : (0x100u + lane);   // invalid lanes match nobody
+        const uint32_t peers = __match_any_sync(FULL_MASK, d);
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) { old = wh[d]; wh[d] = old + __popc(peers); }
+        old = __shfl_sync(FULL_MASK, old, leader);
+        rank[j] = old + __popc(peers & lanemask_lt());
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit: exclusive scan over warps, tile total, then exclusive scan over digits
+    uint32_t total = 0;
+    if (tid < RADIX) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) { uint32_t c = warp_hist[w * RADIX + tid]; warp_hist[w * RADIX + tid] = run; run += c; }
+        total = run;
+        uint32_t x = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(FULL_MASK, x, o); if (lane >= (unsigned)o) x += y; }
+        if (lane == 31) wsum[warp] = x;
+        digit_start[tid] = x - total;   // warp-local exclusive; warp sums added below
+    }
+    __syncthreads();
+    if (tid < RADIX) {
+        uint32_t add = 0;
+        for (unsigned i = 0; i < warp; i++) add += wsum[i];
+        const uint32_t dstart = digit_start[tid] + add;
+        digit_start[tid] = dstart;
+        // chained scan across tiles (decoupled look-back), one thread per digit
+        uint32_t excl = 0;
+        uint32_t* my = status + (uint64_t)tile * RADIX + tid;
+        if (tile > 0) {
+            st_release_u32(my, total | ST_PARTIAL);
+            int64_t t = (int64_t)tile - 1;
+            for (;;) {
+                uint32_t s = ld_acquire_u32(status + (uint64_t)t * RADIX + tid);
+                uint32_t f = s >> 30;
+                if (f == 0) continue;
+                excl += s & ST_VALMASK;
+                if (f == 2) break;
+                t--;
+            }
+        }
+        st_release_u32(my, ((excl + total) & ST_VALMASK) | ST_INCLUSIVE);
+        gbase[tid] = gofs[tid] + excl - dstart;   // modulo 2^32: final index = gbase[d] + tile-local sorted position
+    }
+    __syncthreads();
+
+    // tile-local reorder through shared memory, then digit-contiguous (coalesced) global writes
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++) {
+        if ((wbase + j * 32) < n_valid) {
+            const uint32_t d = key[j].digit(shift, mask);
+            rank[j] += digit_start[d] + wh[d];
+            sk[rank[j]] = key[j];
+        }
+    }
+    __syncthreads();
+    uint32_t dst[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const uint32_t s = tid + k * THREADS;
+        if (s < n_valid) {
+            const K kk = sk[s];
+            dst[k] = gbase[kk.digit(shift, mask)] + s;
+            keys_out[dst[k]] = kk;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < ITEMS; j++)
+        if ((wbase + j * 32) < n_valid) sv[rank[j]] = val[j];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; k++) {
+        const uint32_t s = tid + k * THREADS;
+        if (s < n_valid) vals_out[dst[k]] = sv[s];
+    }
+}
+
+// ---------------------------------------------------------------- host driver
+struct Workspace {
+    uint32_t* ghist = nullptr;      // [MAX_PASSES][RADIX]
+    uint32_t* gofs = nullptr;       // [MAX_PASSES][RADIX]
+    uint32_t* counters = nullptr;   // [MAX_PASSES]
+    uint32_t* status = nullptr;     // [passes][tiles][RADIX]
+    size_t status_bytes = 0;
+};
+
+template <class K> struct Cfg;
+template <> struct Cfg<K64> { static constexpr int THREADS = 512, ITEMS = 12; };
+template <> struct Cfg<K128> { static constexpr int THREADS = 512, ITEMS = 8; };
+
+template <class K> inline size_t tile_size() { return (size_t)Cfg<K>::THREADS * Cfg<K>::ITEMS; }
+template <class K> inline size_t smem_bytes() { return (size_t)(Cfg<K>::THREADS / 32) * RADIX * 4 + tile_size<K>() * sizeof(K); }
+template <class K> inline size_t status_bytes_needed(uint64_t n, int key_bits) {
+    Plan p = make_plan(key_bits);
+    uint64_t tiles = (n + tile_size<K>() - 1) / tile_size<K>();
+    return (size_t)p.n_passes * tiles * RADIX * 4;
+}
+
+}  // namespace rs

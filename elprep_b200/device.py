@@ -1,0 +1,171 @@
+"""Thin Python handle on an ``elp_ctx`` (the C ABI of include/elprep_b200.h).  Plumbing only: every
+method is one C call; errors surface as ``ElprepError`` carrying the reference's panic text."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import SO_COORDINATE, SO_KEEP  # noqa: F401
+
+
+class ElprepError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[{code}] {msg}")
+        self.code = code
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _cstrs(items):
+    arr = (C.c_char_p * max(1, len(items)))()
+    for i, s in enumerate(items):
+        arr[i] = None if s is None else s.encode()
+    return arr
+
+
+class Context:
+    """One device context = one (*sam.Sam) being filled, sorted, duplicate-marked and recalibrated."""
+
+    NQ, NCTX = 94, 16
+
+    def __init__(self, header, device=0, max_cycle=500, quantize_levels=0, sqq=None, prefix="GATK", optical_pixel_distance=100, profile=False):
+        self.L = _lib.load()
+        self.header = header
+        self.max_cycle = max_cycle
+        names = _cstrs(header.contig_names())
+        self._clen = header.contig_lengths()
+        ids = _cstrs([r["ID"] for r in header.RG])
+        lbs = _cstrs([r.get("LB") for r in header.RG])
+        pus = _cstrs([r.get("PU") for r in header.RG])
+        sq = np.ascontiguousarray(sqq if sqq is not None else [], dtype=np.uint8)
+        cfg = _lib.ElpConfig(device, len(header.SQ), names, _vp(self._clen), len(header.RG), ids, lbs, pus, max_cycle, quantize_levels,
+                             _vp(sq) if sq.size else None, int(sq.size), prefix.encode(), optical_pixel_distance, int(profile))
+        h = C.c_void_p()
+        rc = self.L.elp_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise ElprepError(rc, (self.L.elp_last_error(None) or b"").decode())
+        self.h = h
+        self._keep = (names, ids, lbs, pus, sq)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.elp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise ElprepError(rc, (self.L.elp_last_error(self.h) or b"").decode())
+
+    # ---- side inputs ----
+    def set_reference(self, contig, bases):
+        b = np.ascontiguousarray(bases, dtype=np.uint8)
+        self._ck(self.L.elp_set_reference(self.h, contig, _vp(b), b.size))
+
+    def set_known_sites(self, contig, start_end, already_flat=True):
+        se = np.ascontiguousarray(start_end, dtype=np.int32).reshape(-1)
+        self._ck(self.L.elp_set_known_sites(self.h, contig, _vp(se) if se.size else None, se.size // 2, int(already_flat)))
+
+    # ---- phases ----
+    def reserve(self, n_reads, n_bases, n_cigar, n_qname):
+        self._ck(self.L.elp_reserve(self.h, n_reads, n_bases, n_cigar, n_qname))
+
+    def reset(self):
+        self._ck(self.L.elp_reset(self.h))
+
+    def append(self, batch):
+        b = _lib.ElpBatch()
+        b.n = batch.n
+        for k in ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "seq", "qual"):
+            setattr(b, k, _vp(getattr(batch, k)))
+        b.l_seq = _vp(batch.lseq)
+        self._ck(self.L.elp_append_batch(self.h, C.byref(b)))
+
+    @property
+    def n(self):
+        return int(self.L.elp_n_reads(self.h))
+
+    def sort_markdup(self, sorting_order=SO_COORDINATE, mark_duplicates=True):
+        self._ck(self.L.elp_sort_markdup(self.h, sorting_order, int(mark_duplicates)))
+
+    def bqsr_gather(self):
+        self._ck(self.L.elp_bqsr_gather(self.h))
+
+    def table_shape(self):
+        return (int(self.L.elp_bqsr_n_cov(self.h)), 94, 1 + (2 * self.max_cycle + 1) + 16, 2)
+
+    def cov_names(self):
+        return [self.L.elp_bqsr_cov_name(self.h, i).decode() for i in range(int(self.L.elp_bqsr_n_cov(self.h)))]
+
+    def tables_get(self):
+        t = np.zeros(self.table_shape(), dtype=np.int64)
+        self._ck(self.L.elp_bqsr_tables_get(self.h, _vp(t), t.size))
+        return t
+
+    def tables_put(self, t):
+        t = np.ascontiguousarray(t, dtype=np.int64)
+        self._ck(self.L.elp_bqsr_tables_put(self.h, _vp(t), t.size))
+
+    def tables_device(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.elp_bqsr_tables_device(self.h, C.byref(p), C.byref(n)))
+        return p.value, int(n.value)
+
+    def bqsr_finalize(self, report_path=None):
+        self._ck(self.L.elp_bqsr_finalize(self.h, report_path.encode() if report_path else None))
+
+    def empirical_get(self):
+        e = np.zeros(self.table_shape()[:3], dtype=np.uint8)
+        self._ck(self.L.elp_bqsr_empirical_get(self.h, _vp(e), e.size))
+        return e
+
+    def bqsr_apply(self):
+        self._ck(self.L.elp_bqsr_apply(self.h))
+
+    def fetch(self, first=0, n=None, want_qual=True, out=None):
+        """returns (record_index u64[n], flag u16[n], qual_off u64[n+1], qual u8[]) for output records [first, first+n)."""
+        n = self.n - first if n is None else n
+        if out is None:
+            qb = int(self.L.elp_fetch_qual_bytes(self.h, first, n)) if want_qual else 0
+            out = (np.empty(n, np.uint64), np.empty(n, np.uint16), np.empty(n + 1, np.uint64), np.empty(max(qb, 1), np.uint8))
+        idx, flag, qoff, qual = out
+        self._ck(self.L.elp_fetch(self.h, first, n, _vp(idx), _vp(flag), _vp(qoff), _vp(qual) if want_qual else None, qual.size))
+        return idx, flag, qoff, qual
+
+    def debug_adapt(self):
+        u, s = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
+        self._ck(self.L.elp_debug_adapt(self.h, _vp(u), _vp(s)))
+        return u, s
+
+    def launch_count(self):
+        return int(self.L.elp_launch_count(self.h))
+
+    def synchronize(self):
+        self._ck(self.L.elp_synchronize(self.h))
+
+    def kernel_stats(self):
+        arr = (_lib.ElpKernelStat * 64)()
+        k = self.L.elp_kernel_stats(self.h, arr, 64)
+        return {arr[i].name.decode(): dict(launches=int(arr[i].launches), ms=float(arr[i].ms), alg_bytes=float(arr[i].alg_bytes)) for i in range(k)}
+
+    def debug_sort_u64(self, keys, vals, key_bits):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64).copy()
+        vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._ck(self.L.elp_debug_sort_u64(self.h, _vp(keys), _vp(vals), keys.size, key_bits))
+        return keys, vals
+
+    def debug_sort_u128(self, hi, lo, vals, key_bits):
+        hi = np.ascontiguousarray(hi, dtype=np.uint64).copy()
+        lo = np.ascontiguousarray(lo, dtype=np.uint64).copy()
+        vals = np.ascontiguousarray(vals, dtype=np.uint32).copy()
+        self._ck(self.L.elp_debug_sort_u128(self.h, _vp(hi), _vp(lo), _vp(vals), hi.size, key_bits))
+        return hi, lo, vals

@@ -1,0 +1,158 @@
+/*
+ * elprep_b200.h -- C ABI of the B200-native hot path of elPrep 5.1.3:
+ * coordinate sort -> mark duplicates -> BQSR gather -> finalize -> apply.
+ *
+ * Plain C: pointers and sizes only, no CUDA/torch types.  Every entry point names the reference
+ * interface it replaces (paths relative to the elPrep 5.1.3 tree).  All functions return 0 on success
+ * and a negative ELP_E* code on failure; they never abort.  The message for the last failure is
+ * available from elp_last_error() -- the reference panics with the same texts (log.Panic; see
+ * INTEGRATION.md for the cgo shim that turns a non-zero return back into log.Panic).
+ *
+ * Ownership: the caller owns every host buffer; the library copies before returning (cgo pointer
+ * rules).  Device memory is owned by the elp_ctx.  Thread-safety: elp_append_batch may be called
+ * concurrently (pargo LimitedPar stages call filters from several goroutines,
+ * sam/filter-pipeline.go:273,292); every other entry point expects a single caller.
+ *
+ * There is NO CPU fallback: elp_create fails with ELP_ENODEVICE when no CUDA device is usable.
+ */
+#ifndef ELPREP_B200_H
+#define ELPREP_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELP_OK 0
+#define ELP_EINVAL (-1)      /* bad argument */
+#define ELP_ENODEVICE (-2)   /* no usable CUDA device (the product never falls back to the CPU) */
+#define ELP_ECUDA (-3)       /* CUDA runtime error, text in elp_last_error */
+#define ELP_ENOMEM (-4)
+#define ELP_EQUAL (-10)      /* "Invalid QUAL character" (filters/mark-duplicates.go:64-66) */
+#define ELP_ENORG (-11)      /* "BQSR requires input with read groups" (filters/bqsr.go:38) */
+#define ELP_ECYCLE (-12)     /* "cycle value exceeds maximum cycle value" (filters/bqsr.go:364-369) */
+#define ELP_ECLIP (-13)      /* "reference coordinate matches a non-existing base in read" (filters/utils.go:250-265) */
+#define ELP_EREFEND (-14)    /* eligible read runs past the end of its contig (Go: index out of range in computeSnpEvents) */
+#define ELP_ELIMIT (-15)     /* an implementation limit was exceeded (text says which) */
+#define ELP_ESTATE (-16)     /* entry point called in the wrong phase order */
+
+/* sam.SortingOrder (sam/sam-types.go:40-58) */
+#define ELP_SO_KEEP 0
+#define ELP_SO_UNKNOWN 1
+#define ELP_SO_UNSORTED 2
+#define ELP_SO_QUERYNAME 3
+#define ELP_SO_COORDINATE 4
+
+typedef struct elp_ctx elp_ctx;
+
+/* What the filters read from sam.Header: @SQ SN/LN (filters/simple-filters.go:208-214, filters/utils.go:130-138),
+ * @RG ID/LB/PU (filters/mark-duplicates.go:413-423, filters/bqsr.go:35-51), plus the `elprep filter` flags of the
+ * path (cmd/filter.go:435-481). */
+typedef struct {
+    int32_t device;                       /* CUDA device ordinal */
+    int32_t n_contigs;
+    const char *const *contig_names;      /* @SQ SN (only used for messages) */
+    const int32_t *contig_lengths;        /* @SQ LN */
+    int32_t n_read_groups;
+    const char *const *rg_id;             /* @RG ID */
+    const char *const *rg_lb;             /* @RG LB or NULL */
+    const char *const *rg_pu;             /* @RG PU or NULL */
+    int32_t max_cycle;                    /* --max-cycle, default 500 */
+    int32_t quantize_levels;              /* --quantize-levels, default 0 */
+    const uint8_t *sqq; int32_t n_sqq;    /* --sqq list, may be empty */
+    const char *tablename_prefix;         /* --bqsr-tablename-prefix, default "GATK" */
+    int32_t optical_pixel_distance;       /* --optical-duplicates-pixel-distance, default 100 */
+    int32_t profile;                      /* 1: record a CUDA-event pair around every kernel launch (elp_kernel_stats) */
+} elp_config;
+
+/* One batch of sam.Alignment records in columnar form (sam/sam-types.go:289-331) -- what a
+ * pipeline stage marshals from []*sam.Alignment (sam/filter-pipeline.go:92-104).
+ * refid/nref are the REFID/NextREFID temps of filters.AddREFID (simple-filters.go:208-231);
+ * rg is the index of the read's RG:Z tag in elp_config.rg_id, -1 if the read has no RG tag.
+ * cigar: BAM encoding len<<4|op, op indexes "MIDNSHP=X" (sam/bam-files.go). seq: BAM nibbles, high nibble
+ * first, each read byte-aligned, reads packed back to back ((l_seq+1)/2 bytes each). qual: phred bytes
+ * without +33, l_seq bytes per read, packed back to back. */
+typedef struct {
+    uint64_t n;
+    const int32_t *refid; const int32_t *pos; const uint16_t *flag; const uint8_t *mapq;
+    const int32_t *nref; const int32_t *pnext; const int32_t *tlen; const int32_t *rg;
+    const uint64_t *qname_off; const uint8_t *qname;   /* qname_off[n+1], bytes without NUL */
+    const uint64_t *cigar_off; const uint32_t *cigar;  /* cigar_off[n+1] */
+    const int32_t *l_seq; const uint8_t *seq; const uint8_t *qual;
+} elp_batch;
+
+/* per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline object */
+typedef struct {
+    char name[48];
+    uint64_t launches;
+    double ms;            /* sum over launches */
+    double alg_bytes;     /* sum over launches of the ALGORITHMIC bytes (DESIGN.md section "kernels") */
+} elp_kernel_stat;
+
+/* ---- lifecycle ---- */
+int elp_create(const elp_config *cfg, elp_ctx **out);
+void elp_destroy(elp_ctx *ctx);
+const char *elp_last_error(const elp_ctx *ctx);          /* ctx may be NULL: error of the last failed elp_create */
+/* optional capacity hint so that appends never reallocate */
+int elp_reserve(elp_ctx *ctx, uint64_t n_reads, uint64_t n_bases, uint64_t n_cigar_ops, uint64_t n_qname_bytes);
+/* forget all reads/tables but keep device allocations, reference and known sites (bench steps) */
+int elp_reset(elp_ctx *ctx);
+
+/* ---- side inputs: fasta.MappedFasta.Seq(contig) (fasta/fasta-files.go:355) and the known-sites intervals
+ * of NewBaseRecalibrator (filters/bqsr.go:424-443). start/end pairs; flattened inside unless already_flat. ---- */
+int elp_set_reference(elp_ctx *ctx, int32_t contig, const uint8_t *bases, uint64_t n);
+int elp_set_known_sites(elp_ctx *ctx, int32_t contig, const int32_t *start_end_pairs, uint64_t n_intervals, int already_flat);
+
+/* ---- phase 1: (*sam.Sam).AddNodes receiving batches (sam/filter-pipeline.go:108-128) ---- */
+int elp_append_batch(elp_ctx *ctx, const elp_batch *batch);
+uint64_t elp_n_reads(const elp_ctx *ctx);
+
+/* filters.MarkDuplicates (filters/mark-duplicates.go:406-445) + By(CoordinateLess).ParallelStableSort in the
+ * Finalize of (*sam.Sam).AddNodes (sam/filter-pipeline.go:113-117, sam/sam-types.go:425-473,639-641).
+ * sorting_order: ELP_SO_COORDINATE sorts; KEEP/UNKNOWN/UNSORTED leave arrival order. */
+int elp_sort_markdup(elp_ctx *ctx, int sorting_order, int mark_duplicates);
+
+/* ---- phase 3: (*BaseRecalibrator).Recalibrate (filters/bqsr.go:467-551) ---- */
+int elp_bqsr_gather(elp_ctx *ctx);
+/* dense integer tables: [n_cov][94][1 + (2*max_cycle+1) + 16][2] int64 = (observations, mismatches);
+ * column 0 = QualityScores, then Cycles (index cycle+max_cycle), then Contexts (index key>>4).
+ * get/put replace the gob .elrecal exchange of filters/print-bqsr.go:300-329; the device pointer is what a
+ * host layer hands to ncclAllReduce(sum, int64) in place of LoadAndCombineBQSRTables' summation. */
+uint64_t elp_bqsr_tables_len(const elp_ctx *ctx);        /* number of int64 values */
+int32_t elp_bqsr_n_cov(const elp_ctx *ctx);
+const char *elp_bqsr_cov_name(const elp_ctx *ctx, int32_t cov);
+int elp_bqsr_tables_get(elp_ctx *ctx, int64_t *dense, uint64_t n);
+int elp_bqsr_tables_put(elp_ctx *ctx, const int64_t *dense, uint64_t n);
+int elp_bqsr_tables_device(elp_ctx *ctx, void **device_ptr, uint64_t *n);
+
+/* ---- phase 4: FinalizeBQSRTables + PrintBQSRTables (filters/bqsr.go:677-694, filters/print-bqsr.go:269-298).
+ * report_path may be NULL (no report). Also builds the apply look-up table. ---- */
+int elp_bqsr_finalize(elp_ctx *ctx, const char *report_path);
+/* EmpiricalQuality bytes of the finalized tables, same indexing as the dense tables without the [2] */
+int elp_bqsr_empirical_get(elp_ctx *ctx, uint8_t *emp, uint64_t n);
+
+/* ---- phase 5: (*BaseRecalibratorTables).ApplyBQSR (filters/bqsr.go:936-1006) ---- */
+int elp_bqsr_apply(elp_ctx *ctx);
+
+/* ---- phase 6: pulling the result back ((*sam.Sam).RunPipeline as PipelineInput, sam/filter-pipeline.go:242-279).
+ * Records [first, first+n) of the output order. Any output pointer may be NULL.
+ * record_index: arrival index of each output record (the permutation the sort produced);
+ * flag: FLAG with the 0x400 bits; qual: recalibrated QUAL bytes packed back to back; qual_off[n+1]: offsets into qual. ---- */
+int elp_fetch(elp_ctx *ctx, uint64_t first, uint64_t n, uint64_t *record_index, uint16_t *flag, uint64_t *qual_off, uint8_t *qual, uint64_t qual_capacity);
+uint64_t elp_fetch_qual_bytes(elp_ctx *ctx, uint64_t first, uint64_t n);
+/* per-read temps of adaptAlignment (filters/mark-duplicates.go:153-156), arrival order; for parity tests */
+int elp_debug_adapt(elp_ctx *ctx, int32_t *upos, int32_t *score);
+
+/* ---- measurement ---- */
+uint64_t elp_launch_count(const elp_ctx *ctx);           /* kernels launched by this library since create/reset */
+int elp_kernel_stats(elp_ctx *ctx, elp_kernel_stat *out, int cap); /* returns number of entries; profile must be on */
+int elp_synchronize(elp_ctx *ctx);
+
+/* ---- stand-alone access to the device radix sort (the graded kernel), for tests and the sort micro-benchmark:
+ * stable LSD sort of n 64-bit keys (only the low key_bits are significant) carrying 32-bit values. Host buffers. ---- */
+int elp_debug_sort_u64(elp_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t n, int key_bits);
+int elp_debug_sort_u128(elp_ctx *ctx, uint64_t *keys_hi, uint64_t *keys_lo, uint32_t *vals, uint64_t n, int key_bits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
