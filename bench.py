@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""bench.py -- reads/sec through coordinate sort + mark duplicates + BQSR gather/finalize/apply on B200.
+
+One "step" = one pass of the whole hot path over one batch of synthetic 150-bp paired reads:
+  value : whole-job reads/s with the reads already resident in HBM when the timed region starts
+          (elp_sort_markdup + elp_bqsr_gather + [allreduce of the tables at N>1] + elp_bqsr_finalize + elp_bqsr_apply)
+  e2e   : the same metric through the C ABI with HOST buffers: elp_append_batch (H2D from pinned memory) ... elp_fetch (D2H)
+Timing: CUDA events on the library's own stream (elp_timer_start/stop), barrier + synchronize on both sides, max over ranks.
+Each step re-ingests ~270 B/read (>> the 126 MB L2), so no kernel ever sees a warm L2 from the previous step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl reference]
+N>1 is launched by torchrun (one rank per GPU): every rank owns one contig group of an hg38-shaped genome (sfm-style
+partition, cmd/sfm.go; mates never cross groups in this synthetic input), the only collective is one NCCL allreduce
+of the integer BQSR tables.  --impl reference times the CPU restatement of the reference algorithm (oracle/, the Go
+toolchain being absent) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads/sec through sort+markdup+BQSR"
+DEFAULT_READS = 30_000_000          # configs[1] scale (WES-scale 30M reads), with the full sort+markdup+BQSR path of configs[2]
+GENOME_SCALE = 20.0                 # hg38 / 20 = 155 Mbp  ->  30 M x 150 bp = 29x coverage, WGS-30x-like group statistics
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.p = index, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def pinned(batch):
+    """copy the batch columns into page-locked host memory so H2D runs at PCIe speed"""
+    import torch
+    from elprep_b200 import sam
+    kw = {}
+    for f in sam.AlignmentBatch.FIELDS:
+        a = getattr(batch, f)
+        t = torch.empty(a.shape, dtype=getattr(torch, str(a.dtype)) if str(a.dtype) not in ("uint16", "uint32", "uint64") else {"uint16": torch.int16, "uint32": torch.int32, "uint64": torch.int64}[str(a.dtype)], pin_memory=True)
+        v = t.numpy().view(a.dtype)
+        v[...] = a
+        kw[f] = v
+        kw.setdefault("_keep", []).append(t)
+    keep = kw.pop("_keep")
+    b = sam.AlignmentBatch(**kw)
+    b._pinned = keep
+    return b
+
+
+def contig_groups(contigs, n):
+    """sfm-style contig groups (sam/split-merge.go:178-213 balances by contig length): greedy longest-first bin packing"""
+    groups = [[] for _ in range(n)]
+    load = [0] * n
+    for name, ln in sorted(contigs, key=lambda x: -x[1]):
+        k = int(np.argmin(load)); groups[k].append((name, ln)); load[k] += ln
+    return groups
+
+
+def cpu_pipeline(w, n_reads, threads):
+    """the CPU restatement (oracle) over the first n_reads reads: markdup -> sort -> gather -> finalize -> apply"""
+    import oracle
+    b = w.batch.take(np.arange(min(n_reads, w.batch.n)))
+    t0 = time.perf_counter()
+    oracle.mark_duplicates(b, w.header, n_threads=threads)
+    perm = oracle.coordinate_sort(b, n_threads=threads)
+    t1 = time.perf_counter()
+    srt = b.take(perm)            # (*sam.Sam) sorts pointers; materialising the order is not part of the reference's work
+    t2 = time.perf_counter()
+    ref = oracle.Reference(w.header, w.contig_bases, w.sites)
+    t3 = time.perf_counter()
+    tb = oracle.bqsr_gather(srt, w.header, ref, n_threads=threads)
+    oracle.bqsr_finalize(tb)
+    oracle.bqsr_apply(srt, w.header, tb, n_threads=threads)
+    t4 = time.perf_counter()
+    return b.n, (t1 - t0) + (t4 - t3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads", type=int, default=DEFAULT_READS, help="reads per GPU")
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cpu-sample", type=int, default=3_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    from elprep_b200 import synth
+    all_contigs = synth.scaled_hg38(GENOME_SCALE)
+    groups = contig_groups(all_contigs, world)
+    contigs = groups[rank]
+    threads = min(os.cpu_count() or 1, 64)
+    workload_name = f"hg38/{GENOME_SCALE:g}-shaped contig group, {args.reads} synthetic 150-bp paired reads per GPU, sort+markdup+BQSR(gather,finalize,apply)"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_sample = min(args.cpu_sample, args.reads)
+        w = synth.make_workload(n_sample // 2, contigs, seed=20260924, threads=threads)
+        times = []
+        for i in range(args.warmup + args.steps):
+            n, t = cpu_pipeline(w, n_sample, threads)
+            if i >= args.warmup:
+                times.append(t)
+        tt = float(np.sum(times))
+        v = n * len(times) / tt
+        print(json.dumps({"metric": METRIC, "value": v, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": 1e3 * tt / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64",
+                          "data": "synthetic", "impl": "reference", "config": {"workload": workload_name, "flush": "inputs >> L2"},
+                          "cpu_baseline": {"value": v, "unit": "reads/s", "cores": threads, "kind": "port",
+                                           "sample": f"first {n} reads of the workload per step; C restatement of the elPrep 5.1.3 algorithm (oracle/), not the Go binary"},
+                          "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    from elprep_b200 import device
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t0 = time.time()
+    w = synth.make_workload(args.reads // 2, contigs, seed=20260924 + rank, threads=max(4, threads // max(1, world)))
+    log(f"[rank {rank}] generated {w.batch.n} reads over {len(contigs)} contigs in {time.time() - t0:.1f}s")
+    hb = pinned(w.batch)
+    n_reads = hb.n
+    h2d = sum(getattr(hb, f).nbytes for f in hb.FIELDS)
+    ctx = device.Context(w.header, device=local, profile=True)
+    for ci in range(len(contigs)):
+        ctx.set_reference(ci, w.contig_bases[ci])
+        ctx.set_known_sites(ci, w.sites[ci], already_flat=True)
+    ctx.reserve(n_reads, int(hb.qual.size), int(hb.cigar.size), int(hb.qname.size))
+    # pinned output buffers for the fetch
+    out = tuple(torch.empty(s, dtype=dt, pin_memory=True) for s, dt in ((n_reads, torch.int64), (n_reads, torch.int16), (n_reads + 1, torch.int64), (int(hb.qual.size), torch.uint8)))
+    out_np = (out[0].numpy().view(np.uint64), out[1].numpy().view(np.uint16), out[2].numpy().view(np.uint64), out[3].numpy())
+    d2h = sum(a.nbytes for a in out_np)
+    tables_t = None
+    if world > 1:
+        ptr, nvals = ctx.tables_device()
+
+        class _Alias:
+            __cuda_array_interface__ = {"shape": (nvals,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        tables_t = torch.as_tensor(_Alias(), device=f"cuda:{local}")
+
+    def barrier():
+        ctx.synchronize(); torch.cuda.synchronize()
+        if dist:
+            dist.barrier(); torch.cuda.synchronize()
+
+    def step():
+        ctx.reset()
+        barrier()
+        ctx.timer_start()                       # ---- e2e region: host buffers in, host buffers out
+        ctx.append(hb)
+        e_mid = ctx.timer_stop()
+        ctx.timer_start()                       # ---- device-resident region
+        ctx.sort_markdup(device.SO_COORDINATE, True)
+        ctx.bqsr_gather()
+        if dist:
+            ctx.tables_device()
+            dist.all_reduce(tables_t); torch.cuda.synchronize()
+        ctx.bqsr_finalize(None)
+        ctx.bqsr_apply()
+        t_dev = ctx.timer_stop()
+        ctx.timer_start()
+        ctx.fetch(0, n_reads, True, out_np)
+        e_out = ctx.timer_stop()
+        return t_dev, e_mid + t_dev + e_out
+
+    for _ in range(args.warmup):
+        step()
+    ctx.reset_stats()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    dev_ms, e2e_ms = [], []
+    for _ in range(args.steps):
+        a, b = step()
+        dev_ms.append(a); e2e_ms.append(b)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count()
+    stats = ctx.kernel_stats()
+    tot = torch.tensor([float(np.sum(dev_ms)), float(np.sum(e2e_ms))], device=f"cuda:{local}", dtype=torch.float64)
+    cnt = torch.tensor([float(n_reads)], device=f"cuda:{local}", dtype=torch.float64)
+    if dist:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_total_ms, e2e_total_ms = tot.tolist()
+    total_reads = cnt.item()
+    if rank != 0:
+        if dist:
+            dist.barrier(); dist.destroy_process_group()
+        return
+    value = total_reads * args.steps / (dev_total_ms / 1e3)
+    e2e = total_reads * args.steps / (e2e_total_ms / 1e3)
+    # roofline of the dominant kernel (largest summed device time over the timed steps)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
+    dom = max(stats.items(), key=lambda kv: kv[1]["ms"]) if stats else (None, None)
+    roof = None
+    if dom[0]:
+        k = dom[1]
+        ach = k["alg_bytes"] / (k["ms"] / 1e3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "launches": k["launches"], "avg_launch_ms": k["ms"] / max(1, k["launches"]), "alg_bytes_per_launch": k["alg_bytes"] / max(1, k["launches"])}
+    kern = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                "GBps": (v["alg_bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["alg_bytes"] > 0 else None} for n, v in sorted(stats.items(), key=lambda kv: -kv[1]["ms"])}
+    cpu = None
+    if not args.no_cpu_baseline:
+        n_s, t_s = cpu_pipeline(w, args.cpu_sample, threads)
+        cpu = {"value": n_s / t_s, "unit": "reads/s", "cores": threads, "kind": "port",
+               "sample": f"first {n_s} reads of rank 0's workload, one pass; C restatement of the elPrep 5.1.3 algorithm (oracle/), not the Go binary"}
+    line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
+            "config": {"workload": workload_name, "reads_per_gpu": n_reads, "parallelism": f"contig-group x{world}", "flush": "inputs >> L2 (re-ingested every step)"},
+            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps},
+            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": kern}
+    print(json.dumps(line))
+    if dist:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

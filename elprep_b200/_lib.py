@@ -33,7 +33,7 @@ EXPORTS = ["elp_create", "elp_destroy", "elp_last_error", "elp_reserve", "elp_re
            "elp_append_batch", "elp_n_reads", "elp_sort_markdup", "elp_bqsr_gather", "elp_bqsr_tables_len", "elp_bqsr_n_cov",
            "elp_bqsr_cov_name", "elp_bqsr_tables_get", "elp_bqsr_tables_put", "elp_bqsr_tables_device", "elp_bqsr_finalize",
            "elp_bqsr_empirical_get", "elp_bqsr_apply", "elp_fetch", "elp_fetch_qual_bytes", "elp_debug_adapt", "elp_launch_count",
-           "elp_kernel_stats", "elp_synchronize", "elp_debug_sort_u64", "elp_debug_sort_u128"]
+           "elp_kernel_stats", "elp_synchronize", "elp_reset_stats", "elp_timer_start", "elp_timer_stop", "elp_debug_sort_u64", "elp_debug_sort_u128"]
 
 _lib = None
 
@@ -80,6 +80,9 @@ def load():
     L.elp_debug_adapt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.elp_kernel_stats.argtypes = [C.c_void_p, C.POINTER(ElpKernelStat), C.c_int]
     L.elp_synchronize.argtypes = [C.c_void_p]
+    L.elp_reset_stats.argtypes = [C.c_void_p]
+    L.elp_timer_start.argtypes = [C.c_void_p]
+    L.elp_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.elp_debug_sort_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     L.elp_debug_sort_u128.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     _lib = L

@@ -134,6 +134,7 @@ void elp_destroy(elp_ctx* c) {
     c->s_flag.release(); c->s_mapq.release(); c->s_qual_off.release(); c->s_seq_off.release(); c->s_cigar_off.release(); c->s_out_off.release(); c->s_ncigar.release(); c->qual_out.release();
     for (auto& pe : c->pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -356,6 +357,23 @@ int elp_debug_adapt(elp_ctx* c, int32_t* upos, int32_t* score) {
 
 uint64_t elp_launch_count(const elp_ctx* c) { return c ? c->launches : 0; }
 int elp_synchronize(elp_ctx* c) { if (!c) return ELP_EINVAL; cudaSetDevice(c->device); CUDA_TRY(c, cudaStreamSynchronize(c->stream)); return ELP_OK; }
+int elp_reset_stats(elp_ctx* c) { if (!c) return ELP_EINVAL; cudaSetDevice(c->device); c->resolve_events(); c->stats.clear(); c->launches = 0; return ELP_OK; }
+int elp_timer_start(elp_ctx* c) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (!c->timer_a) { CUDA_TRY(c, cudaEventCreate(&c->timer_a)); CUDA_TRY(c, cudaEventCreate(&c->timer_b)); }
+    CUDA_TRY(c, cudaEventRecord(c->timer_a, c->stream));
+    return ELP_OK;
+}
+int elp_timer_stop(elp_ctx* c, double* ms) {
+    if (!c || !ms || !c->timer_a) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    CUDA_TRY(c, cudaEventRecord(c->timer_b, c->stream));
+    CUDA_TRY(c, cudaEventSynchronize(c->timer_b));
+    float f = 0; CUDA_TRY(c, cudaEventElapsedTime(&f, c->timer_a, c->timer_b));
+    *ms = f;
+    return ELP_OK;
+}
 int elp_kernel_stats(elp_ctx* c, elp_kernel_stat* out, int cap) {
     if (!c) return 0;
     cudaSetDevice(c->device);

@@ -129,6 +129,7 @@ struct elp_ctx {
     std::map<std::string, KernelStat> stats;
     std::vector<PendingEvent> pending;
     std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
 
     int fail(int code, const char* fmt, ...) {
         char buf[1024];

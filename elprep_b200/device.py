@@ -152,6 +152,17 @@ class Context:
     def synchronize(self):
         self._ck(self.L.elp_synchronize(self.h))
 
+    def reset_stats(self):
+        self._ck(self.L.elp_reset_stats(self.h))
+
+    def timer_start(self):
+        self._ck(self.L.elp_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.L.elp_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
     def kernel_stats(self):
         arr = (_lib.ElpKernelStat * 64)()
         k = self.L.elp_kernel_stats(self.h, arr, 64)

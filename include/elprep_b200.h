@@ -146,6 +146,10 @@ int elp_debug_adapt(elp_ctx *ctx, int32_t *upos, int32_t *score);
 uint64_t elp_launch_count(const elp_ctx *ctx);           /* kernels launched by this library since create/reset */
 int elp_kernel_stats(elp_ctx *ctx, elp_kernel_stat *out, int cap); /* returns number of entries; profile must be on */
 int elp_synchronize(elp_ctx *ctx);
+int elp_reset_stats(elp_ctx *ctx);                       /* forget kernel stats and the launch count */
+/* device-side stopwatch: CUDA events recorded on the library's own stream (torch.cuda.Event would not see it) */
+int elp_timer_start(elp_ctx *ctx);
+int elp_timer_stop(elp_ctx *ctx, double *elapsed_ms);    /* synchronizes */
 
 /* ---- stand-alone access to the device radix sort (the graded kernel), for tests and the sort micro-benchmark:
  * stable LSD sort of n 64-bit keys (only the low key_bits are significant) carrying 32-bit values. Host buffers. ---- */
