@@ -21,8 +21,6 @@ struct ApplyArgs {
     uint32_t* err;
 };
 
-__device__ __forceinline__ int nib_at(const uint8_t* seq, uint64_t soff, int i) { const uint8_t b = seq[soff + (uint64_t)(i >> 1)]; return (i & 1) ? (b & 15) : (b >> 4); }
-__device__ __forceinline__ int nib_index(int nib) { return nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : -1; }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bqsr_apply_kernel(ApplyArgs A) {
     const unsigned lane = lane_id();
@@ -39,34 +37,51 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bqsr_apply_kernel(ApplyA
     }
     if (!recal) { for (int i = lane; i < L; i += 32) A.out[ooff + i] = A.qual[qoff + i]; return; }
     const uint16_t f = A.flag[k];
-    const uint64_t soff = A.seq_off[k];
-    // low-quality tails on the FULL read (computeStrandedClippedSeq, bqsr.go:312-331)
+    const uint8_t* seqp = A.seq + A.seq_off[k]; const uint8_t* qualp = A.qual + qoff; uint8_t* outp = A.out + ooff;
+    // low-quality tails on the FULL read (computeStrandedClippedSeq, bqsr.go:312-331), via ballots
+    const int nit = (L + 31) >> 5;
     int leftPos = L, rightPos = -1;
-    for (int i = lane; i < L; i += 32) if (A.qual[qoff + i] > 2) { leftPos = min(leftPos, i); rightPos = max(rightPos, i); }
-    for (int o = 16; o; o >>= 1) { leftPos = min(leftPos, __shfl_xor_sync(FULL_MASK, leftPos, o)); rightPos = max(rightPos, __shfl_xor_sync(FULL_MASK, rightPos, o)); }
+    for (int it = 0; it < nit; it++) {
+        const int i = lane + it * 32;
+        const unsigned b = __ballot_sync(FULL_MASK, i < L && qualp[i] > 2);
+        if (b) { if (leftPos == L) leftPos = it * 32 + __ffs(b) - 1; rightPos = it * 32 + 31 - __clz(b); }
+    }
     const int reversed = (f & F_REVERSED) ? 1 : 0, last = (f & F_LAST) ? 1 : 0;
     const int rof = 1 - 2 * last, cf = rof + reversed * (L - 1) * rof, inc = (1 - 2 * reversed) * rof;   // bqsr.go:376-383
-    const int ncyc = 2 * A.lut_maxcyc + 1;
+    const uint32_t ncyc = 2u * (uint32_t)A.lut_maxcyc + 1u;
+    const uint8_t* lut_cov = A.lut + (size_t)cov * 94u * ncyc * 17u;
     uint32_t errbits = 0;
-    for (int i = lane; i < L; i += 32) {
-        uint8_t q = A.qual[qoff + i];
-        if (q >= 6) {                                              // minInterestingQual
-            if (q > 93) errbits |= DERR_QUAL_RANGE;
-            else {
-                const int cyc = cf + i * inc;
-                if (cyc > A.max_cycle || cyc < -A.max_cycle) errbits |= DERR_CYCLE;   // checkCycleCovariate :364-369
-                else {
-                    int ctx = 16;                                  // 16 = no context (key -1)
-                    const int bi = nib_index(nib_at(A.seq, soff, i));
-                    if (bi >= 0) {
-                        if (!reversed) { if (i >= 1 && i - 1 >= leftPos && i <= rightPos) { const int pb = nib_index(nib_at(A.seq, soff, i - 1)); if (pb >= 0) ctx = pb | (bi << 2); } }
-                        else { if (i + 1 <= L - 1 && i >= leftPos && i + 1 <= rightPos) { const int nb = nib_index(nib_at(A.seq, soff, i + 1)); if (nb >= 0) ctx = (3 - nb) | ((3 - bi) << 2); } }
-                    }
-                    q = A.lut[(((size_t)cov * 94 + q) * ncyc + (size_t)(cyc + A.lut_maxcyc)) * 17 + ctx];
-                }
-            }
+    // branch-free inner loop: base index via popc/ffs on the BAM nibble, the neighbouring base through a warp shuffle
+    // (one extra byte load only on the lane at the 32-base boundary), LUT address in 32-bit arithmetic
+    const int dirn = reversed ? 1 : -1;                    // context neighbour: previous base in sequencing direction
+    for (int it = 0; it < nit; it++) {
+        const int i = lane + it * 32;
+        const bool in = i < L;
+        const int ic = in ? i : L - 1;
+        uint32_t q = qualp[ic];
+        const uint32_t sb = seqp[ic >> 1];
+        const uint32_t nib = (ic & 1) ? (sb & 15u) : (sb >> 4);
+        const int bi = (__popc(nib) == 1) ? (__ffs(nib) - 1) : -1;
+        // neighbour base index: lane+dirn in this iteration, or the boundary base of the adjacent iteration
+        int nbi = __shfl_sync(FULL_MASK, bi, (lane + dirn) & 31);
+        const int ni = ic + dirn;
+        if (((int)lane + dirn) < 0 || ((int)lane + dirn) > 31 || ni >= L) {
+            if (ni >= 0 && ni < L) { const uint32_t nb = seqp[ni >> 1]; const uint32_t nn = (ni & 1) ? (nb & 15u) : (nb >> 4); nbi = (__popc(nn) == 1) ? (__ffs(nn) - 1) : -1; }
+            else nbi = -1;
         }
-        A.out[ooff + i] = q;
+        // both bases inside [leftPos, rightPos] (tails with QUAL <= 2 read as N) and both ACGT
+        const int lo_i = reversed ? ic : ni, hi_i = reversed ? ni : ic;
+        const bool okc = (bi >= 0) & (nbi >= 0) & (lo_i >= leftPos) & (hi_i <= rightPos) & (ni >= 0) & (ni < L);
+        const uint32_t ctx = okc ? (reversed ? (uint32_t)((3 - nbi) | ((3 - bi) << 2)) : (uint32_t)(nbi | (bi << 2))) : 16u;
+        const int cyc = cf + ic * inc;
+        const bool recal_b = q >= 6;
+        const bool badq = q > 93, badc = (cyc > A.max_cycle) | (cyc < -A.max_cycle);
+        if (recal_b & in & (badq | badc)) errbits |= badq ? DERR_QUAL_RANGE : DERR_CYCLE;
+        const uint32_t qi = badq ? 93u : q;
+        const int cyi = badc ? 0 : cyc;
+        const uint32_t nq = lut_cov[(qi * ncyc + (uint32_t)(cyi + A.lut_maxcyc)) * 17u + ctx];
+        if (recal_b & !badq & !badc) q = nq;
+        if (in) outp[i] = (uint8_t)q;
     }
     for (int o = 16; o; o >>= 1) errbits |= __shfl_xor_sync(FULL_MASK, errbits, o);
     if (errbits && lane == 0) atomicOr(A.err, errbits);

@@ -98,8 +98,8 @@ static __global__ void rs_scan_kernel(const uint32_t* __restrict__ ghist, uint32
 }
 
 // ---------------------------------------------------------------- one digit pass
-template <class K, int THREADS, int ITEMS>
-__global__ void __launch_bounds__(THREADS) rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
+template <class K, int THREADS, int ITEMS, int MIN_CTAS>
+__global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
                                                               const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
                                                               uint64_t n, int shift, int bits, const uint32_t* __restrict__ gofs,
                                                               uint32_t* __restrict__ status, uint32_t* __restrict__ tile_counter) {
@@ -121,12 +121,12 @@ __global__ void __launch_bounds__(THREADS) rs_onesweep_kernel(const K* __restric
 
     // warp-striped loads: element (warp, j, lane) <-> tile index warp*ITEMS*32 + j*32 + lane (stable order = that index)
     K key[ITEMS];
-    uint32_t val[ITEMS], rank[ITEMS];
+    uint32_t rank[ITEMS];
     const uint32_t wbase = warp * ITEMS * 32 + lane;
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         uint32_t t = wbase + j * 32;
-        if (t < n_valid) { key[j] = K::load(keys_in + base + t); val[j] = ld_stream_u32(vals_in + base + t); }
+        if (t < n_valid) key[j] = K::load(keys_in + base + t);
     }
     uint32_t* wh = warp_hist + warp * RADIX;
 #pragma unroll
@@ -136,10 +136,9 @@ __global__ void __launch_bounds__(THREADS) rs_onesweep_kernel(const K* __restric
         const uint32_t peers = __match_any_sync(FULL_MASK, d);
         const uint32_t leader = __ffs(peers) - 1;
         uint32_t old = 0;
-        if (valid && lane == leader) { old = wh[d]; wh[d] = old + __popc(peers); }
+        if (valid && lane == leader) old = atomicAdd(&wh[d], (uint32_t)__popc(peers));   // shared atomics of one warp retire in issue order: no barrier between items
         old = __shfl_sync(FULL_MASK, old, leader);
         rank[j] = old + __popc(peers & lanemask_lt());
-        __syncwarp();
     }
     __syncthreads();
 
@@ -205,7 +204,7 @@ __global__ void __launch_bounds__(THREADS) rs_onesweep_kernel(const K* __restric
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < ITEMS; j++)
-        if ((wbase + j * 32) < n_valid) sv[rank[j]] = val[j];
+        if ((wbase + j * 32) < n_valid) sv[rank[j]] = ld_stream_u32(vals_in + base + wbase + j * 32);   // payload is loaded late: fewer live registers -> more CTAs per SM
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
@@ -224,8 +223,8 @@ struct Workspace {
 };
 
 template <class K> struct Cfg;
-template <> struct Cfg<K64> { static constexpr int THREADS = 512, ITEMS = 12; };
-template <> struct Cfg<K128> { static constexpr int THREADS = 512, ITEMS = 8; };
+template <> struct Cfg<K64> { static constexpr int THREADS = 256, ITEMS = 12, MIN_CTAS = 4; };
+template <> struct Cfg<K128> { static constexpr int THREADS = 256, ITEMS = 8, MIN_CTAS = 4; };
 
 template <class K> inline size_t tile_size() { return (size_t)Cfg<K>::THREADS * Cfg<K>::ITEMS; }
 template <class K> inline size_t smem_bytes() { return (size_t)(Cfg<K>::THREADS / 32) * RADIX * 4 + tile_size<K>() * sizeof(K); }

@@ -44,7 +44,7 @@ int radix_sort_impl(elp_ctx* c, K* ka, K* kb, uint32_t* va, uint32_t* vb, uint64
         c->end();
         LAUNCH_CHECK(c);
     }
-    auto kern = rs_onesweep_kernel<K, Cfg<K>::THREADS, Cfg<K>::ITEMS>;
+    auto kern = rs_onesweep_kernel<K, Cfg<K>::THREADS, Cfg<K>::ITEMS, Cfg<K>::MIN_CTAS>;
     const size_t smem = smem_bytes<K>();
     static bool attr_set = false;   // per template instantiation
     if (!attr_set) { CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }

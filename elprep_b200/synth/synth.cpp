@@ -70,6 +70,7 @@ struct Gen {
         double g = std::sqrt(-2.0 * std::log(1.0 - r.uni())) * std::cos(6.283185307179586 * r.uni());
         int ins = (int)std::lround(400.0 + 60.0 * g);
         ins = std::max(60, std::min(1000, ins));
+        if (r.uni() < 0.02) ins = 60 + (int)r.below(90);   // short inserts: reads run into the adaptor (exercises hardClipAdaptorSequence)
         double u = r.uni() * total_len;
         int c = (int)(std::upper_bound(cum.begin(), cum.end(), u) - cum.begin()) - 1;
         c = std::max(0, std::min(P.n_contigs - 1, c));
