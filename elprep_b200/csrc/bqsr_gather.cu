@@ -1,11 +1,17 @@
 // bqsr_gather.cu -- BQSR covariate gather on the device (replaces (*BaseRecalibrator).Recalibrate,
 // filters/bqsr.go:467-551, with the read clipping of filters/utils.go:130-534).
 //
-// One warp per read, in output (coordinate) order so that reference bases are fetched from HBM once and re-used
-// through L2.  Lane 0 performs the (short, serial) CIGAR surgery of hardClipAdaptorSequence /
-// hardClipSoftClippedBases on a shared-memory copy of the CIGAR; all 32 lanes then walk the kept bases:
-// mismatch vs reference (computeSnpEvents :254-285), known-sites mask (calculateSkipSlice :389-414), cycle
-// (:376-387) and 2-mer context (:64-146,312-362) covariates, and the three integer tables.
+// Two kernels over the reads in output (coordinate) order:
+//   bqsr_prep_kernel   one THREAD per read: recalibrateAln eligibility (:225-244), hardClipAdaptorSequence and
+//                      hardClipSoftClippedBases on a private copy of the CIGAR (utils.go:148-534), the known-sites
+//                      intersection and its read coordinates (calculateSkipSlice :389-414).  The serial, branchy CIGAR
+//                      surgery runs 32 reads per warp instead of one; the result is a 32-byte descriptor per read.
+//   bqsr_count_kernel  one WARP per read, one lane per base: mismatch vs reference (computeSnpEvents :254-285), cycle
+//                      (:376-387) and 2-mer context (:64-146,312-362) covariates, and the table updates.  Observation
+//                      counters of the frequent QUAL values are privatised in shared memory per CTA (persistent CTAs,
+//                      flushed once with 64-bit atomics); mismatches (rare) and infrequent QUAL values go to the global table.
+// Kept bases keep their original alignment under hard clipping, so reference positions come from the ORIGINAL CIGAR
+// offset by the clip start; only the known-sites mask needs the clipped CIGAR (its coordinate mapping has quirks).
 // Table layout: dense int64 [n_cov][94][1 + (2*max_cycle+1) + 16][2] = (observations, mismatches); the
 // QualityScores column is derived as the row sum of the Cycles columns (every counted base updates both).
 #include <algorithm>
@@ -157,6 +163,17 @@ __device__ void hard_clip(Clip& a, int start, int stop) {
     if (start == 0) a.pos += shift;
 }
 
+// ---------------------------------------------------------------- per-read descriptor written by the prep kernel
+struct __align__(16) ReadDesc {
+    int32_t c_pos;            // POS after clipping (1-based)
+    uint16_t c_s0, c_len;     // kept bases [c_s0, c_s0 + c_len) of the original read; c_len == 0: not recalibrated
+    uint8_t flags, cov, n_skip, pad;
+    uint32_t ovf;             // slot of the 512-bit skip bitmask when more than 4 known-site ranges hit the read
+    uint16_t skip[4][2];      // inclusive [first,last] clipped read coordinates masked by known sites
+};
+constexpr uint8_t DF_REVERSED = 1, DF_LAST = 2, DF_SINGLE_M = 4, DF_SKIP_OVF = 8;
+constexpr int OVF_WORDS = 16;   // 512 bits
+
 struct GatherArgs {
     uint64_t n;
     const int32_t *refid, *pos, *nref, *pnext, *tlen, *rg, *lseq; const uint16_t* flag; const uint8_t* mapq;
@@ -167,281 +184,245 @@ struct GatherArgs {
     const uint8_t* const* ref; const uint64_t* ref_len;
     const int32_t* const* sites; const uint64_t* n_sites;
     TableGeom geom; unsigned long long* tables; uint32_t* err;
+    ReadDesc* desc; uint32_t* ovf_bits; uint32_t* ovf_count; uint32_t ovf_cap;
     // shared-memory privatisation: observation counters of the frequent QUAL values live in shared memory
     int8_t qslot[94]; uint8_t slot_q[94]; int n_slots, Lc, ncols_s;
 };
 
-__device__ __forceinline__ int nib_at(const uint8_t* seq, uint64_t soff, int i) { const uint8_t b = seq[soff + (uint64_t)(i >> 1)]; return (i & 1) ? (b & 15) : (b >> 4); }
-__device__ __forceinline__ int nib_index(int nib) { return nib == 1 ? 0 : nib == 2 ? 1 : nib == 4 ? 2 : nib == 8 ? 3 : -1; }   // A C G T, else -1
-__device__ __forceinline__ int ref_class(uint8_t b) {   // baseToIntMap, bqsr.go:247-252 (0 for N and IUPAC codes)
-    switch (b) { case 'a': case 'A': case '*': return 1; case 'c': case 'C': return 2; case 'g': case 'G': return 3; case 't': case 'T': return 4; }
-    return 0;
-}
-
-// observation / mismatch update of one table cell: hot QUAL values go to the CTA's shared-memory table (flushed once at
-// the end), everything else and all (rare) mismatch counts go straight to the global int64 table
-__device__ __forceinline__ void count_cell(const GatherArgs& A, uint32_t* sm_tab, int cov, int q, int col_s, int col_g, int snp) {
-    const int slot = A.qslot[q];
-    if (slot >= 0) atomicAdd(&sm_tab[((size_t)cov * A.n_slots + slot) * A.ncols_s + col_s], 1u);
-    else atomicAdd(A.tables + 2 * A.geom.idx(cov, q, col_g), 1ull);
-    if (snp) atomicAdd(A.tables + 2 * A.geom.idx(cov, q, col_g) + 1, 1ull);
-}
-
-__device__ __forceinline__ void gather_read(const GatherArgs& A, const uint64_t k, const unsigned lane, const unsigned w, uint32_t* cg, uint32_t* tmp_cg,
-                                            int* sfs, int* sfe, uint32_t* sm_tab) {
-    // ---- recalibrateAln, bqsr.go:225-244 (all lanes evaluate the same scalars) ----
+// ---------------------------------------------------------------- kernel A: one thread per read
+__global__ void __launch_bounds__(128) bqsr_prep_kernel(GatherArgs A) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= A.n) return;
+    ReadDesc d; d.c_pos = 0; d.c_s0 = 0; d.c_len = 0; d.flags = 0; d.cov = 0; d.n_skip = 0; d.pad = 0; d.ovf = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) { d.skip[r][0] = 0; d.skip[r][1] = 0; }
+    ReadDesc* out = A.desc + k;
+    auto done = [&]() { *reinterpret_cast<uint4*>(out) = *reinterpret_cast<const uint4*>(&d); *(reinterpret_cast<uint4*>(out) + 1) = *(reinterpret_cast<const uint4*>(&d) + 1); };
+    // ---- recalibrateAln, bqsr.go:225-244 ----
     const uint16_t f = A.flag[k];
     const uint8_t mq = A.mapq[k];
     const int32_t refid = A.refid[k], pos0 = A.pos[k], g = A.rg[k], L0 = A.lseq[k];
     const int nc0 = (int)A.ncigar[k];
-    if (!(mq > 0 && mq < 255)) return;
-    if (f & (F_SECONDARY | F_DUPLICATE | F_QCFAILED)) return;
-    if ((f & F_UNMAPPED) || refid < 0 || pos0 == 0) return;          // isStrictUnmapped, utils.go:140
-    if (pos0 <= 0 || L0 <= 0) return;
-    if (g < 0 || g >= A.n_rg) return;                               // aln.RG() != nil
-    if (refid >= A.n_contigs || pos0 > A.contig_len[refid]) return;  // alignmentAgreesWithHeader, utils.go:130-138
-    int c_pos = pos0, c_nc = nc0, c_s0 = 0, c_len = L0, c_err = 0;
+    bool elig = (mq > 0 && mq < 255) && !(f & (F_SECONDARY | F_DUPLICATE | F_QCFAILED)) && !((f & F_UNMAPPED) || refid < 0 || pos0 == 0) && pos0 > 0 && L0 > 0 &&
+                g >= 0 && g < A.n_rg && refid < A.n_contigs;
+    if (elig && pos0 > A.contig_len[refid]) elig = false;            // alignmentAgreesWithHeader, utils.go:130-138
+    if (!elig) { done(); return; }
+    if (nc0 > MAXC) { atomicOr(A.err, DERR_CIGAR_LIMIT); done(); return; }
+    uint32_t cg[MAXC + 4], tmp[MAXC + 4];
     const uint64_t coff = A.cigar_off[k];
-    const uint32_t op0 = nc0 > 0 ? A.cigar[coff] : 0u;
-    bool fast = false;
-    if (nc0 == 1 && op_of(op0) == 0) {
-        // ---- fast path: a single M operation (the common case). No soft clips; the adaptor boundary test of
-        // hardClipAdaptorSequence (utils.go:148-222) and the resulting clip have closed forms here ----
-        if (len_of(op0) != L0) return;                                   // SEQ length != read length from the CIGAR
+    int bad = 0, rl = 0;
+    for (int i = 0; i < nc0; i++) { const uint32_t op = A.cigar[coff + i]; cg[i] = op; const int o = op_of(op); bad |= (o == 3); rl += cons_read(o) * len_of(op); }
+    if (bad || rl != L0) { done(); return; }                        // no N operation; SEQ length == read length from the CIGAR
+    Clip a; a.pos = pos0; a.nc = nc0; a.s0 = 0; a.slen = L0; a.err = 0; a.cg = cg; a.tmp = tmp;
+    {
         const int32_t pnext = A.pnext[k], tlen = A.tlen[k], nref = A.nref[k];
-        const bool next_unmapped = (f & F_NEXTUNMAPPED) || nref < 0 || pnext == 0;
+        // hardClipAdaptorSequence, utils.go:148-222
+        bool well = false; int alnEnd = -1;
+        const bool next_unmapped = (f & F_NEXTUNMAPPED) || nref < 0 || pnext == 0;   // isStrictNextUnmapped, utils.go:144
         if (tlen != 0 && (f & F_MULTIPLE) && !next_unmapped && (((f & F_REVERSED) != 0) != ((f & F_NEXTREVERSED) != 0))) {
-            const int alnEnd = pos0 + L0 - 1;
-            const bool well = (f & F_REVERSED) ? (alnEnd > pnext) : (pos0 <= pnext + tlen);
+            if (f & F_REVERSED) { alnEnd = aln_end(a); well = alnEnd > pnext; }
+            else well = pos0 <= pnext + tlen;
+        }
+        if (well) {
             const int boundary = (f & F_REVERSED) ? (int)pnext - 1 : (int)pos0 + (tlen < 0 ? -tlen : tlen);
-            if (well && boundary >= pos0 && boundary <= alnEnd) {
-                const int goal = boundary - pos0;                          // read coordinate of the boundary (utils.go:267-349 for one M op)
-                if (f & F_REVERSED) { c_s0 = goal + 1; c_len = L0 - goal - 1; c_pos = pos0 + goal + 1; }   // hardClip(0, goal)
-                else { c_len = goal; }                                     // hardClip(goal, L-1); goal == 0 clips everything
-            }
-        }
-        if (c_len <= 0) return;
-        if (lane == 0) cg[0] = mk(c_len, 0);
-        c_nc = 1;
-        fast = true;
-        __syncwarp();
-    }
-    if (!fast) {
-        if (nc0 > MAXC) { if (lane == 0) atomicOr(A.err, DERR_CIGAR_LIMIT); return; }
-        for (int i = lane; i < nc0; i += 32) cg[i] = A.cigar[coff + i];
-        __syncwarp();
-        // no N operation, SEQ length == read length from the CIGAR
-        int bad = 0, rl = 0;
-        for (int i = lane; i < nc0; i += 32) { const int o = op_of(cg[i]); bad |= (o == 3); rl += cons_read(o) * len_of(cg[i]); }
-        for (int o = 16; o; o >>= 1) { bad |= __shfl_xor_sync(FULL_MASK, bad, o); rl += __shfl_xor_sync(FULL_MASK, rl, o); }
-        if (bad || rl != L0) return;
-
-        // ---- clipping on lane 0 ----
-        if (lane == 0) {
-            Clip a; a.pos = pos0; a.nc = nc0; a.s0 = 0; a.slen = L0; a.err = 0; a.cg = cg; a.tmp = tmp_cg;
-            const int32_t pnext = A.pnext[k], tlen = A.tlen[k], nref = A.nref[k];
-            // hardClipAdaptorSequence, utils.go:148-222
-            bool well = false; int alnEnd = -1;
-            const bool next_unmapped = (f & F_NEXTUNMAPPED) || nref < 0 || pnext == 0;   // isStrictNextUnmapped, utils.go:144
-            if (tlen != 0 && (f & F_MULTIPLE) && !next_unmapped && (((f & F_REVERSED) != 0) != ((f & F_NEXTREVERSED) != 0))) {
-                if (f & F_REVERSED) { alnEnd = aln_end(a); well = alnEnd > pnext; }
-                else well = pos0 <= pnext + tlen;
-            }
-            if (well) {
-                const int boundary = (f & F_REVERSED) ? (int)pnext - 1 : (int)pos0 + (tlen < 0 ? -tlen : tlen);
-                if (boundary >= pos0) {
-                    if (alnEnd < 0) alnEnd = aln_end(a);
-                    if (boundary <= alnEnd) {
-                        bool ok;
-                        if (f & F_REVERSED) { const int stop = get_read_coord(a.cg, a.nc, soft_start(a), boundary, false, &ok); if (!ok) a.err = 2; else hard_clip(a, 0, stop); }
-                        else { const int start = get_read_coord(a.cg, a.nc, soft_start(a), boundary, true, &ok); if (!ok) a.err = 2; else hard_clip(a, start, a.slen - 1); }
-                    }
+            if (boundary >= pos0) {
+                if (alnEnd < 0) alnEnd = aln_end(a);
+                if (boundary <= alnEnd) {
+                    bool ok;
+                    if (f & F_REVERSED) { const int stop = get_read_coord(a.cg, a.nc, soft_start(a), boundary, false, &ok); if (!ok) a.err = 2; else hard_clip(a, 0, stop); }
+                    else { const int start = get_read_coord(a.cg, a.nc, soft_start(a), boundary, true, &ok); if (!ok) a.err = 2; else hard_clip(a, start, a.slen - 1); }
                 }
             }
-            // hardClipSoftClippedBases, utils.go:506-534
-            if (!a.err && a.slen > 0) {
-                int readIndex = 0, cutLeft = -1, cutRight = -1; bool rightTail = false;
-                for (int i = 0; i < a.nc; i++) {
-                    const int o = op_of(a.cg[i]), ln = len_of(a.cg[i]);
-                    if (o == 4) { if (rightTail) cutRight = readIndex; else cutLeft = readIndex + ln - 1; }
-                    else if (o != 5) rightTail = true;
-                    readIndex += cons_read(o) * ln;
-                }
-                if (cutRight >= 0) hard_clip(a, cutRight, a.slen - 1);
-                if (!a.err && a.slen > 0 && cutLeft >= 0) hard_clip(a, 0, cutLeft);
-            }
-            c_pos = a.pos; c_nc = a.nc; c_s0 = a.s0; c_len = a.slen; c_err = a.err;
         }
-    c_pos = __shfl_sync(FULL_MASK, c_pos, 0); c_nc = __shfl_sync(FULL_MASK, c_nc, 0); c_s0 = __shfl_sync(FULL_MASK, c_s0, 0);
-        c_len = __shfl_sync(FULL_MASK, c_len, 0); c_err = __shfl_sync(FULL_MASK, c_err, 0);
-        __syncwarp();
+        // hardClipSoftClippedBases, utils.go:506-534
+        if (!a.err && a.slen > 0) {
+            int readIndex = 0, cutLeft = -1, cutRight = -1; bool rightTail = false;
+            for (int i = 0; i < a.nc; i++) {
+                const int o = op_of(a.cg[i]), ln = len_of(a.cg[i]);
+                if (o == 4) { if (rightTail) cutRight = readIndex; else cutLeft = readIndex + ln - 1; }
+                else if (o != 5) rightTail = true;
+                readIndex += cons_read(o) * ln;
+            }
+            if (cutRight >= 0) hard_clip(a, cutRight, a.slen - 1);
+            if (!a.err && a.slen > 0 && cutLeft >= 0) hard_clip(a, 0, cutLeft);
+        }
     }
-    if (c_err) { if (lane == 0) atomicOr(A.err, DERR_CLIP); return; }
-    if (c_len == 0) return;
-    if (c_len > 32 * MAXIT) { if (lane == 0) atomicOr(A.err, DERR_READLEN_LIMIT); return; }
-    const int L = c_len;
-    const uint64_t qoff = A.qual_off[k] + (uint64_t)c_s0, soff = A.seq_off[k];
-    const int cov = A.rg_cov[g];
-
-    // ---- low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2, via ballots ----
-    const int nit = (L + 31) >> 5;
-    int leftPos = L, rightPos = -1;
-    for (int it = 0; it < nit; it++) {
-        const int i = lane + it * 32;
-        const unsigned b = __ballot_sync(FULL_MASK, i < L && A.qual[qoff + i] > 2);
-        if (b) { if (leftPos == L) leftPos = it * 32 + __ffs(b) - 1; rightPos = it * 32 + 31 - __clz(b); }
-    }
-    const bool have_ctx = leftPos <= rightPos;
-
-    // ---- known sites (calculateSkipSlice, bqsr.go:389-414): clipped read has no S, so softStart/softEnd = POS / End ----
-    uint32_t skipmask = 0;   // bit it: base lane+32*it is masked
-    const uint32_t ns = (uint32_t)A.n_sites[refid];
-    const bool single_m = (c_nc == 1 && (op_of(cg[0]) == 0 || op_of(cg[0]) == 7 || op_of(cg[0]) == 8)) ||
-                          (c_nc == 2 && ((op_of(cg[0]) == 5 && op_of(cg[1]) == 0) || (op_of(cg[0]) == 0 && op_of(cg[1]) == 5))) ||
-                          (c_nc == 3 && op_of(cg[0]) == 5 && op_of(cg[1]) == 0 && op_of(cg[2]) == 5);
+    if (a.err) { atomicOr(A.err, DERR_CLIP); done(); return; }
+    if (a.slen <= 0) { done(); return; }
+    if (a.slen > 32 * MAXIT) { atomicOr(A.err, DERR_READLEN_LIMIT); done(); return; }
+    const int L = a.slen;
+    // is the clipped CIGAR a single M-type operation (plus hard clips)?
+    int n_m = 0, n_other = 0;
+    for (int i = 0; i < a.nc; i++) { const int o = op_of(a.cg[i]); if (o == 0 || o == 7 || o == 8) n_m++; else if (o != 5) n_other++; }
+    d.c_pos = a.pos; d.c_s0 = (uint16_t)a.s0; d.c_len = (uint16_t)L; d.cov = (uint8_t)A.rg_cov[g];
+    d.flags = ((f & F_REVERSED) ? DF_REVERSED : 0) | ((f & F_LAST) ? DF_LAST : 0) | ((n_m == 1 && n_other == 0) ? DF_SINGLE_M : 0);
+    // ---- known sites (calculateSkipSlice, bqsr.go:389-414): the clipped read has no S, so softStart/softEnd = POS / End ----
+    const uint64_t ns = A.n_sites[refid];
     if (ns) {
         const int32_t* sv = A.sites[refid];
-        int refl;
-        if (single_m) refl = L;
-        else {
-            refl = 0;
-            for (int i = lane; i < c_nc; i += 32) refl += cons_ref(op_of(cg[i])) * len_of(cg[i]);
-            for (int o = 16; o; o >>= 1) refl += __shfl_xor_sync(FULL_MASK, refl, o);
-        }
-        const int ss = c_pos, se = c_pos + refl - 1;
-        // intervals.Intersect (intervals/intervals.go:166-173): s0 = first interval with End >= ss (32-ary search), then the
-        // run of intervals with Start <= se
-        uint32_t lo = 0, hi = ns;   // invariant: End[i] < ss for i < lo, End[i] >= ss for i >= hi
-        while (lo < hi) {
-            const uint32_t span = hi - lo, step = (span + 31) >> 5;
-            const uint32_t probe = lo + lane * step;
-            const bool inr = probe < hi;
-            const unsigned bm = __ballot_sync(FULL_MASK, inr && sv[2 * probe + 1] >= ss);
-            const unsigned vm = __ballot_sync(FULL_MASK, inr);
-            if (bm) { const uint32_t f1 = __ffs(bm) - 1; hi = lo + f1 * step; lo = f1 ? lo + (f1 - 1) * step + 1 : lo; }
-            else { lo = lo + (uint32_t)(__popc(vm) - 1) * step + 1; }
-            if (lo > hi) lo = hi;
-        }
-        const uint32_t s0 = lo;
-        uint32_t s1 = s0;
+        int refl = 0;
+        for (int i = 0; i < a.nc; i++) refl += cons_ref(op_of(a.cg[i])) * len_of(a.cg[i]);
+        const int ss = a.pos, se = a.pos + refl - 1;
+        // intervals.Intersect, intervals/intervals.go:166-173
+        uint64_t lo = 0, hi = ns;
+        while (lo < hi) { const uint64_t m = (lo + hi) >> 1; if (!(sv[2 * m + 1] >= ss)) lo = m + 1; else hi = m; }
+        const uint64_t s0 = lo;
+        uint64_t s1 = s0;
         while (s1 < ns && sv[2 * s1] <= se) s1++;
-        for (uint32_t sb = s0; sb < s1; sb += 32) {
-            const uint32_t sidx = sb + lane;
-            if (sidx < s1) {
-                bool ok; int fs = get_read_coord(cg, c_nc, ss, sv[2 * sidx], false, &ok);
+        if (s1 - s0 <= 4) {
+            for (uint64_t s = s0; s < s1; s++) {
+                bool ok; int fs = get_read_coord(a.cg, a.nc, ss, sv[2 * s], false, &ok);
                 if (!ok || fs < 0) fs = 0;
-                int fe = get_read_coord(cg, c_nc, ss, sv[2 * sidx + 1], false, &ok);
+                int fe = get_read_coord(a.cg, a.nc, ss, sv[2 * s + 1], false, &ok);
                 if (!ok || fe > L - 1) fe = L - 1;
-                sfs[lane] = fs; sfe[lane] = fe;
+                if (fs <= fe) { d.skip[d.n_skip][0] = (uint16_t)fs; d.skip[d.n_skip][1] = (uint16_t)fe; d.n_skip++; }
             }
-            __syncwarp();
-            const int cnt = (s1 - sb) < 32 ? (int)(s1 - sb) : 32;
-            for (int it = 0; it < nit; it++) {
-                const int i = lane + it * 32;
-                for (int q = 0; q < cnt; q++) if (i >= sfs[q] && i <= sfe[q]) skipmask |= 1u << it;
-            }
-            __syncwarp();
-        }
-    }
-
-    // ---- per base ----
-    const uint8_t* ref = A.ref[refid]; const int64_t reflen = (int64_t)A.ref_len[refid];
-    const int reversed = (f & F_REVERSED) ? 1 : 0, last = (f & F_LAST) ? 1 : 0;
-    const int rof = 1 - 2 * last, cf = rof + reversed * (L - 1) * rof, inc = (1 - 2 * reversed) * rof;   // prepareCycleCovariates, bqsr.go:376-383
-    const int lead_h = (single_m && op_of(cg[0]) == 5) ? 1 : 0;   // index of the M op in the single-M fast path
-    (void)lead_h;
-    const uint32_t sm_base = (uint32_t)cov * (uint32_t)A.n_slots * (uint32_t)A.ncols_s;
-    const uint8_t* seqp = A.seq + soff; const uint8_t* qualp = A.qual + qoff;
-    uint32_t errbits = 0;
-    const int dirn = reversed ? 1 : -1;                    // context neighbour: previous base in sequencing direction
-    const int64_t j0 = (int64_t)c_pos - 1;
-    for (int it = 0; it < nit; it++) {
-        const int i = lane + it * 32;
-        const bool in = i < L;
-        const int ic = in ? i : L - 1;
-        const int oi = c_s0 + ic;
-        const uint32_t sb = seqp[oi >> 1];
-        const uint32_t nib = (oi & 1) ? (sb & 15u) : (sb >> 4);
-        const int bi = (__popc(nib) == 1) ? (__ffs(nib) - 1) : -1;      // A C G T -> 0..3, everything else -1 (bqsr.go:509)
-        const int q = qualp[ic];
-        // neighbour base (sequencing direction) through a shuffle; one extra load on the lane at a 32-base boundary
-        int nbi = __shfl_sync(FULL_MASK, bi, (lane + dirn) & 31);
-        const int ni = ic + dirn;
-        if (((int)lane + dirn) < 0 || ((int)lane + dirn) > 31 || ni >= L) {
-            if (ni >= 0 && ni < L) { const int on = c_s0 + ni; const uint32_t nb = seqp[on >> 1]; const uint32_t nn = (on & 1) ? (nb & 15u) : (nb >> 4); nbi = (__popc(nn) == 1) ? (__ffs(nn) - 1) : -1; }
-            else nbi = -1;
-        }
-        const bool counted = in & !((skipmask >> it) & 1) & (bi >= 0) & (q >= 6);   // bqsr.go:506-515
-        if (!counted) continue;
-        if (q > 93) { errbits |= DERR_QUAL_RANGE; continue; }
-        // reference position of base i (computeSnpEvents, bqsr.go:254-285)
-        int64_t jj = -1;
-        if (single_m) jj = j0 + ic;
-        else {
-            int ri = 0; int64_t j = j0;
-            for (int c = 0; c < c_nc; c++) {
-                const int o = op_of(cg[c]), ln = len_of(cg[c]);
-                if (o == 0 || o == 7 || o == 8) { if (ic < ri + ln) { jj = j + (ic - ri); break; } ri += ln; j += ln; }
-                else if (o == 2 || o == 3) j += ln;
-                else if (o == 1 || o == 4) { if (ic < ri + ln) break; ri += ln; }
-            }
-        }
-        int snp = 0;
-        if (jj >= 0) {
-            if (jj >= reflen) { errbits |= DERR_REFEND; continue; }
-            // baseToIntMap (bqsr.go:247-252): A/a/* C/c G/g T/t are classes, everything else is class 0 (never equals an ACGT read base)
-            uint32_t u = ref[jj]; if (u == '*') u = 'A';
-            u &= 0xDFu;
-            const uint32_t x = u - 'A';
-            const bool rvalid = x < 32 && ((0x00080045u >> x) & 1);      // A, C, G, T
-            uint32_t ridx = (u >> 1) & 3; ridx ^= ridx >> 1;             // A0 C1 G2 T3
-            snp = !(rvalid && (int)ridx == bi);
-        }
-        const int cyc = cf + ic * inc;
-        if (cyc > A.geom.max_cycle || cyc < -A.geom.max_cycle) { errbits |= DERR_CYCLE; continue; }
-        // context: 2-mer in sequencing direction; key>>4 = prev | cur<<2 (keyFromContext, bqsr.go:64-76); tails with QUAL<=2 read as N
-        const int lo_i = reversed ? ic : ni, hi_i = reversed ? ni : ic;
-        const bool okc = have_ctx & (nbi >= 0) & (lo_i >= leftPos) & (hi_i <= rightPos) & (ni >= 0) & (ni < L);
-        const int ctx = okc ? (reversed ? ((3 - nbi) | ((3 - bi) << 2)) : (nbi | (bi << 2))) : -1;
-        const int slot = A.qslot[q];
-        if (slot >= 0) {
-            const uint32_t row = sm_base + (uint32_t)slot * (uint32_t)A.ncols_s;
-            atomicAdd(&sm_tab[row + (uint32_t)(cyc + A.Lc)], 1u);
-            if (ctx >= 0) atomicAdd(&sm_tab[row + (uint32_t)(2 * A.Lc + 1 + ctx)], 1u);
         } else {
-            atomicAdd(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_cycle(cyc)), 1ull);
-            if (ctx >= 0) atomicAdd(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_ctx(ctx)), 1ull);
-        }
-        if (snp) {   // mismatches are rare: straight to the global table
-            atomicAdd(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_cycle(cyc)) + 1, 1ull);
-            if (ctx >= 0) atomicAdd(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_ctx(ctx)) + 1, 1ull);
+            const uint32_t slot = atomicAdd(A.ovf_count, 1u);
+            if (slot >= A.ovf_cap) { atomicOr(A.err, DERR_READLEN_LIMIT); done(); return; }
+            uint32_t bits[OVF_WORDS];
+            for (int i = 0; i < OVF_WORDS; i++) bits[i] = 0;
+            for (uint64_t s = s0; s < s1; s++) {
+                bool ok; int fs = get_read_coord(a.cg, a.nc, ss, sv[2 * s], false, &ok);
+                if (!ok || fs < 0) fs = 0;
+                int fe = get_read_coord(a.cg, a.nc, ss, sv[2 * s + 1], false, &ok);
+                if (!ok || fe > L - 1) fe = L - 1;
+                for (int i = fs; i <= fe; i++) bits[i >> 5] |= 1u << (i & 31);
+            }
+            for (int i = 0; i < OVF_WORDS; i++) A.ovf_bits[(size_t)slot * OVF_WORDS + i] = bits[i];
+            d.flags |= DF_SKIP_OVF; d.ovf = slot;
         }
     }
-    for (int o = 16; o; o >>= 1) errbits |= __shfl_xor_sync(FULL_MASK, errbits, o);
-    if (errbits && lane == 0) atomicOr(A.err, errbits);
+    done();
 }
 
-// persistent kernel: every warp walks reads k = warp, warp + W, ... in output order (W consecutive reads are in flight chip-wide,
-// so reference bases stay L2-resident); the CTA's shared-memory table is flushed once with 64-bit global atomics
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bqsr_gather_kernel(GatherArgs A) {
+// ---------------------------------------------------------------- kernel B: one warp per read, one lane per base
+// base code of a BAM nibble: A C G T -> 0..3, everything else 8 (bit 3 = "not ACGT", bqsr.go:509)
+__device__ __forceinline__ uint32_t nib_code(uint32_t nib) { return (uint32_t)((0x8888888388828108ull >> (4 * nib)) & 0xfull); }
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bqsr_count_kernel(GatherArgs A) {
     extern __shared__ uint32_t sm_tab[];
-    __shared__ uint32_t sh_cg[WARPS_PER_BLOCK][MAXC + 4];
-    __shared__ uint32_t sh_tmp[WARPS_PER_BLOCK][MAXC + 4];
-    __shared__ int sh_fs[WARPS_PER_BLOCK][32], sh_fe[WARPS_PER_BLOCK][32];
+    __shared__ uint8_t sm_refcode[256];   // baseToIntMap (bqsr.go:247-252): A/a/* C/c G/g T/t -> 0..3, everything else 8
+    __shared__ int8_t sm_qslot[96];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
     const int cells = A.geom.n_cov * A.n_slots * A.ncols_s;
     for (int i = threadIdx.x; i < cells; i += blockDim.x) sm_tab[i] = 0;
+    {
+        const int b = threadIdx.x; uint8_t c = 8;
+        if (b == 'A' || b == 'a' || b == '*') c = 0; else if (b == 'C' || b == 'c') c = 1; else if (b == 'G' || b == 'g') c = 2; else if (b == 'T' || b == 't') c = 3;
+        sm_refcode[b] = c;
+        if (b < 96) sm_qslot[b] = b < 94 ? A.qslot[b] : (int8_t)-1;
+    }
     __syncthreads();
+    const int Lc = A.Lc, ncols_s = A.ncols_s, max_cycle = A.geom.max_cycle;
     for (uint64_t k = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + w; k < A.n; k += (uint64_t)gridDim.x * WARPS_PER_BLOCK) {
-        gather_read(A, k, lane, w, sh_cg[w], sh_tmp[w], sh_fs[w], sh_fe[w], sm_tab);
-        __syncwarp();
+        // descriptor: two 16-byte loads, broadcast to the warp
+        const uint4 d0 = *reinterpret_cast<const uint4*>(A.desc + k);
+        const int L = (int)(d0.y >> 16);
+        if (L == 0) continue;
+        const uint4 d1 = *(reinterpret_cast<const uint4*>(A.desc + k) + 1);
+        const int c_pos = (int)d0.x, c_s0 = (int)(d0.y & 0xffff);
+        const uint32_t flags = d0.z & 0xff, cov = (d0.z >> 8) & 0xff, n_skip = (d0.z >> 16) & 0xff;
+        const int reversed = (flags & DF_REVERSED) ? 1 : 0, last = (flags & DF_LAST) ? 1 : 0;
+        const int32_t refid = A.refid[k];
+        const uint8_t* qualp = A.qual + A.qual_off[k] + c_s0;
+        const uint8_t* seqp = A.seq + A.seq_off[k];
+        const uint8_t* ref = A.ref[refid]; const int64_t reflen = (int64_t)A.ref_len[refid];
+        const int nit = (L + 31) >> 5;
+        // low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2
+        int leftPos = L, rightPos = -1;
+        for (int it = 0; it < nit; it++) {
+            const int i = lane + it * 32;
+            const unsigned b = __ballot_sync(FULL_MASK, i < L && qualp[i] > 2);
+            if (b) { if (leftPos == L) leftPos = it * 32 + __ffs(b) - 1; rightPos = it * 32 + 31 - __clz(b); }
+        }
+        // a base has a context iff it and its predecessor in sequencing direction lie inside [leftPos, rightPos]:
+        //   forward: i-1 >= leftPos, i <= rightPos ; reverse: i >= leftPos, i+1 <= rightPos
+        const int wlo = reversed ? leftPos : leftPos + 1, whi = reversed ? rightPos - 1 : rightPos;
+        const uint32_t wspan = (whi >= wlo) ? (uint32_t)(whi - wlo) : 0u;
+        const bool have_win = whi >= wlo;
+        const int rof = 1 - 2 * last, cf = rof + reversed * (L - 1) * rof, inc = (1 - 2 * reversed) * rof;   // prepareCycleCovariates, bqsr.go:376-383
+        const uint32_t cmask = reversed ? 3u : 0u;
+        const uint32_t row0 = cov * (uint32_t)A.n_slots;
+        const bool single_m = (flags & DF_SINGLE_M) != 0;
+        const int64_t j0 = (int64_t)c_pos - 1;
+        // general CIGAR: reference positions from the ORIGINAL alignment (kept bases keep their positions under hard clipping)
+        int32_t pos_orig = 0; uint64_t coff = 0; int nc = 0;
+        if (!single_m) { pos_orig = A.pos[k]; coff = A.cigar_off[k]; nc = (int)A.ncigar[k]; }
+        uint32_t errbits = 0;
+        uint32_t carry = 8;   // code of the base just before this iteration's first lane, in sequencing direction
+        for (int t = 0; t < nit; t++) {
+            const int it = reversed ? nit - 1 - t : t;                   // walk in sequencing direction
+            const int i = lane + it * 32;
+            const bool in = i < L;
+            const int ic = in ? i : L - 1;
+            const int oi = c_s0 + ic;
+            const uint32_t sb = seqp[oi >> 1];
+            const uint32_t nib = (oi & 1) ? (sb & 15u) : (sb >> 4);
+            const uint32_t code = in ? nib_code(nib) : 8u;               // read-orientation code
+            const uint32_t q = qualp[ic];
+            // predecessor in sequencing direction: lane-1 (forward) / lane+1 (reverse); across the 32-base boundary via `carry`
+            uint32_t pcode = __shfl_sync(FULL_MASK, code, reversed ? (lane + 1) & 31 : (lane - 1) & 31);
+            if (lane == (reversed ? 31u : 0u)) pcode = carry;
+            carry = __shfl_sync(FULL_MASK, code, reversed ? 0 : 31);
+            // skip mask
+            bool skipped = false;
+            if (n_skip) {
+                const uint32_t sk[4] = {d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int r = 0; r < 4; r++) if (r < (int)n_skip) skipped |= ((uint32_t)ic >= (sk[r] & 0xffff)) & ((uint32_t)ic <= (sk[r] >> 16));
+            } else if (flags & DF_SKIP_OVF) skipped = (A.ovf_bits[(size_t)d0.w * OVF_WORDS + (ic >> 5)] >> (ic & 31)) & 1;
+            const bool counted = in & !skipped & !(code & 8) & (q >= 6);   // bqsr.go:506-515
+            if (!__any_sync(FULL_MASK, counted)) continue;
+            if (counted && q > 93) { errbits |= DERR_QUAL_RANGE; }
+            // reference base (computeSnpEvents, bqsr.go:254-285)
+            int64_t jj = -1;
+            if (single_m) jj = j0 + ic;
+            else {
+                const int oi2 = oi; int ri = 0; int64_t j = (int64_t)pos_orig - 1;
+                for (int c = 0; c < nc; c++) {
+                    const uint32_t op = A.cigar[coff + c]; const int o = op_of(op), ln = len_of(op);
+                    if (o == 0 || o == 7 || o == 8) { if (oi2 < ri + ln) { jj = j + (oi2 - ri); break; } ri += ln; j += ln; }
+                    else if (o == 2 || o == 3) j += ln;
+                    else if (o == 1 || o == 4) { if (oi2 < ri + ln) break; ri += ln; }
+                }
+            }
+            uint32_t snp = 0;
+            if (counted && jj >= 0) {
+                if (jj >= reflen) { errbits |= DERR_REFEND; }
+                else snp = sm_refcode[ref[jj]] != code;
+            }
+            const int cyc = cf + ic * inc;
+            const bool badc = (cyc > max_cycle) | (cyc < -max_cycle);                     // checkCycleCovariate :364-369
+            if (counted & badc) errbits |= DERR_CYCLE;
+            const uint32_t qq = q > 93 ? 93u : q;
+            const int slot = sm_qslot[qq];
+            const bool okc = counted & !(pcode & 8) & have_win & ((uint32_t)(ic - wlo) <= wspan);
+            const uint32_t ctx = ((pcode ^ cmask) & 3u) | (((code ^ cmask) & 3u) << 2);   // key>>4 = prev | cur<<2 (bqsr.go:64-76), complemented for reverse reads
+            if (counted && q <= 93 && !badc) {
+                if (slot >= 0) {
+                    const uint32_t row = (row0 + (uint32_t)slot) * (uint32_t)ncols_s;
+                    atomicAdd(&sm_tab[row + (uint32_t)(cyc + Lc)], 1u);
+                    if (okc) atomicAdd(&sm_tab[row + (uint32_t)(2 * Lc + 1) + ctx], 1u);
+                } else {
+                    atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_cycle(cyc)), 1ull);
+                    if (okc) atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_ctx((int)ctx)), 1ull);
+                }
+                if (snp) {   // mismatches are rare: straight to the global table
+                    atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_cycle(cyc)) + 1, 1ull);
+                    if (okc) atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_ctx((int)ctx)) + 1, 1ull);
+                }
+            }
+        }
+        errbits = __reduce_or_sync(FULL_MASK, errbits);
+        if (errbits && lane == 0) atomicOr(A.err, errbits);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
         const uint32_t v = sm_tab[i];
         if (!v) continue;
-        const int col_s = i % A.ncols_s, cs = i / A.ncols_s, slot = cs % A.n_slots, cov = cs / A.n_slots;
-        const int col_g = col_s < 2 * A.Lc + 1 ? A.geom.col_cycle(col_s - A.Lc) : A.geom.col_ctx(col_s - (2 * A.Lc + 1));
+        const int col_s = i % ncols_s, cs = i / ncols_s, slot = cs % A.n_slots, cov = cs / A.n_slots;
+        const int col_g = col_s < 2 * Lc + 1 ? A.geom.col_cycle(col_s - Lc) : A.geom.col_ctx(col_s - (2 * Lc + 1));
         atomicAdd(A.tables + 2 * A.geom.idx(cov, A.slot_q[slot], col_g), (unsigned long long)v);
     }
 }
@@ -515,11 +496,22 @@ int phase_bqsr_gather(elp_ctx* c) {
         }
         const size_t smem = (size_t)c->geom.n_cov * A.n_slots * A.ncols_s * 4;
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        // descriptors (32 B/read) and the overflow skip bitmasks live in scratch buffers that are free in this phase
+        CUDA_TRY(c, c->keys_a.reserve(n * 4 + 8, c->stream));
+        A.desc = reinterpret_cast<ReadDesc*>(c->keys_a.p);
+        A.ovf_cap = (uint32_t)std::min<uint64_t>(n, (n >> 4) + 4096);
+        CUDA_TRY(c, c->vals_a.reserve((size_t)A.ovf_cap * OVF_WORDS + 8, c->stream));
+        A.ovf_bits = c->vals_a.p;
+        A.ovf_count = c->scan_tmp.p;   // one u32, zeroed below
+        CUDA_TRY(c, cudaMemsetAsync(A.ovf_count, 0, 4, c->stream));
+        c->begin("bqsr_prep", (double)n * (4 * 7 + 2 + 1 + 8 + 4 + 32) + (double)c->n_cigar * 4);
+        bqsr_prep_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(A);
+        c->end(); LAUNCH_CHECK(c);
         uint64_t grid = std::min<uint64_t>((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (uint64_t)sms * 4);
         grid = std::max<uint64_t>(grid, (n + (4u << 20) - 1) / (4u << 20));   // <= 4 M reads per CTA keeps the 32-bit shared counters far from overflow
-        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
         c->begin("bqsr_gather", bytes);
-        bqsr_gather_kernel<<<(unsigned)grid, WARPS_PER_BLOCK * 32, smem, c->stream>>>(A);
+        bqsr_count_kernel<<<(unsigned)grid, WARPS_PER_BLOCK * 32, smem, c->stream>>>(A);
         c->end(); LAUNCH_CHECK(c);
     }
     c->begin("bqsr_derive_q", 0);
