@@ -12,6 +12,7 @@
 #include <cfloat>
 #include <cstdio>
 #include <string>
+#include <thread>
 #include <vector>
 #include "ctx.h"
 #include "gomath.hpp"
@@ -224,6 +225,15 @@ int write_report(elp_ctx* c, const Tables& T, const std::vector<uint8_t>& emp, c
     return E_OK;
 }
 
+// run f(i) for i in [0,n) on a few host threads (the per-entry posteriors are independent)
+template <class F> void host_parallel_for(int n, F f) {
+    const int nt = std::max(1, std::min<int>({8, (int)std::thread::hardware_concurrency(), n}));
+    if (nt == 1) { for (int i = 0; i < n; i++) f(i); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back([=]() { for (int i = t; i < n; i += nt) f(i); });
+    for (auto& x : th) x.join();
+}
+
 }  // namespace
 
 int phase_bqsr_finalize(elp_ctx* c, const char* report_path) {
@@ -236,10 +246,13 @@ int phase_bqsr_finalize(elp_ctx* c, const char* report_path) {
     Tables T{g, c->h_tables.data()};
     // FinalizeBQSRTables: EmpiricalQuality of every existing entry with prior = its reported qual (:677-694)
     c->h_emp.assign(cells, 0);
-    for (int cv = 0; cv < g.n_cov; cv++) for (int q = 0; q < 94; q++) for (int col = 0; col < g.ncols(); col++) {
-        const int64_t o = T.obs(cv, q, col);
-        if (o > 0) c->h_emp[g.idx(cv, q, col)] = Entry(o, T.mis(cv, q, col)).empirical((double)q);
-    }
+    host_parallel_for(g.n_cov * 94, [&](int row) {
+        const int cv = row / 94, q = row % 94;
+        for (int col = 0; col < g.ncols(); col++) {
+            const int64_t o = T.obs(cv, q, col);
+            if (o > 0) c->h_emp[g.idx(cv, q, col)] = Entry(o, T.mis(cv, q, col)).empirical((double)q);
+        }
+    });
     std::vector<Combined> comb(g.n_cov);
     for (int cv = 0; cv < g.n_cov; cv++) comb[cv] = combine(T, cv);
     if (report_path) { int rc = write_report(c, T, c->h_emp, comb, report_path); if (rc) return rc; }
@@ -253,38 +266,44 @@ int phase_bqsr_finalize(elp_ctx* c, const char* report_path) {
     const int ncyc = 2 * Lc + 1;
     std::vector<uint8_t> lut((size_t)g.n_cov * 94 * ncyc * 17, 0);
     std::vector<uint8_t> cov_exists(g.n_cov, 0);
+    std::vector<double> dGv(g.n_cov, 0.0);
     for (int cv = 0; cv < g.n_cov; cv++) {
         if (!comb[cv].exists) continue;
         cov_exists[cv] = 1;
-        const double eps = comb[cv].reported;   // globalQualityScorePrior = -1 -> always the read group's reportedQuality (:959-964)
-        const double dG = (double)Entry(comb[cv].obs, comb[cv].mis).empirical(eps) - eps;
-        for (int q = 6; q < 94; q++) {
-            double dQ = 0;
-            if (T.obs(cv, q, 0) > 0) dQ = (double)Entry(T.obs(cv, q, 0), T.mis(cv, q, 0)).empirical(dG + eps) - dG - eps;
-            const double cp = dQ + dG + eps;
-            double dctx[17]; bool hctx[17];
-            for (int x = 0; x < 16; x++) { const int col = g.col_ctx(x); hctx[x] = T.obs(cv, q, col) > 0; dctx[x] = hctx[x] ? (double)Entry(T.obs(cv, q, col), T.mis(cv, q, col)).empirical(cp) - cp : 0.0; }
-            hctx[16] = false; dctx[16] = 0;
-            for (int cy = -Lc; cy <= Lc; cy++) {
-                const int col = g.col_cycle(cy);
-                const bool hc = T.obs(cv, q, col) > 0;
-                const double dcy = hc ? (double)Entry(T.obs(cv, q, col), T.mis(cv, q, col)).empirical(cp) - cp : 0.0;
-                uint8_t* dst = &lut[(((size_t)cv * 94 + q) * ncyc + (size_t)(cy + Lc)) * 17];
-                for (int x = 0; x < 17; x++) {
-                    double dC = 0;
-                    if (hc) dC = dcy;
-                    if (hctx[x]) dC += dctx[x];
-                    const double est = cp + dC;
-                    int r = (int)gomath::Round(est); r = std::max(1, std::min(r, 93));
-                    uint8_t nq = quant[r];
-                    if (have_stat) nq = stat[nq];
-                    dst[x] = nq;
-                }
+        // globalQualityScorePrior = -1 -> epsilon is always the read group's reportedQuality (:959-964)
+        dGv[cv] = (double)Entry(comb[cv].obs, comb[cv].mis).empirical(comb[cv].reported) - comb[cv].reported;
+    }
+    host_parallel_for(g.n_cov * 88, [&](int job) {
+        const int cv = job / 88, q = 6 + job % 88;
+        if (!comb[cv].exists) return;
+        const double eps = comb[cv].reported, dG = dGv[cv];
+        double dQ = 0;
+        if (T.obs(cv, q, 0) > 0) dQ = (double)Entry(T.obs(cv, q, 0), T.mis(cv, q, 0)).empirical(dG + eps) - dG - eps;
+        const double cp = dQ + dG + eps;
+        auto final_q = [&](double est) { int r = (int)gomath::Round(est); r = std::max(1, std::min(r, 93)); uint8_t nq = quant[r]; if (have_stat) nq = stat[nq]; return nq; };
+        uint8_t* row = &lut[((size_t)cv * 94 + q) * ncyc * 17];
+        if (T.obs(cv, q, 0) <= 0) { std::memset(row, final_q(cp + 0.0), (size_t)ncyc * 17); return; }   // QUAL never observed: no cycle/context entries either
+        double dctx[17]; bool hctx[17];
+        for (int x = 0; x < 16; x++) { const int col = g.col_ctx(x); hctx[x] = T.obs(cv, q, col) > 0; dctx[x] = hctx[x] ? (double)Entry(T.obs(cv, q, col), T.mis(cv, q, col)).empirical(cp) - cp : 0.0; }
+        hctx[16] = false; dctx[16] = 0;
+        for (int cy = -Lc; cy <= Lc; cy++) {
+            const int col = g.col_cycle(cy);
+            const bool hc = T.obs(cv, q, col) > 0;
+            const double dcy = hc ? (double)Entry(T.obs(cv, q, col), T.mis(cv, q, col)).empirical(cp) - cp : 0.0;
+            uint8_t* dst = row + (size_t)(cy + Lc) * 17;
+            for (int x = 0; x < 17; x++) {
+                double dC = 0;
+                if (hc) dC = dcy;
+                if (hctx[x]) dC += dctx[x];
+                dst[x] = final_q(cp + dC);
             }
         }
+    });
+    if (c->lut_cap < lut.size() + 16) {
+        if (c->d_lut) { cudaFree(c->d_lut); c->d_lut = nullptr; }
+        CUDA_TRY(c, cudaMalloc(&c->d_lut, lut.size() + 16));
+        c->lut_cap = lut.size() + 16;
     }
-    if (c->d_lut) { cudaFree(c->d_lut); c->d_lut = nullptr; }
-    CUDA_TRY(c, cudaMalloc(&c->d_lut, lut.size() + 16));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice, c->stream));
     if (!c->d_cov_exists) CUDA_TRY(c, cudaMalloc(&c->d_cov_exists, std::max(1, g.n_cov)));
     CUDA_TRY(c, cudaMemcpyAsync(c->d_cov_exists, cov_exists.data(), g.n_cov, cudaMemcpyHostToDevice, c->stream));

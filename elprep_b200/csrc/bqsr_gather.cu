@@ -22,7 +22,10 @@ namespace {
 
 constexpr int MAXC = 64;        // CIGAR operations per read handled by the kernel
 constexpr int MAXIT = 16;       // 32*MAXIT = 512 bases per clipped read (cycles beyond max_cycle=500 are an error anyway)
-constexpr int WARPS_PER_BLOCK = 8;
+#ifndef EXP_WARPS
+#define EXP_WARPS 8
+#endif
+constexpr int WARPS_PER_BLOCK = EXP_WARPS;
 
 __device__ __forceinline__ int op_of(uint32_t c) { return (int)(c & 15); }
 __device__ __forceinline__ int len_of(uint32_t c) { return (int)(c >> 4); }
@@ -300,26 +303,154 @@ __global__ void __launch_bounds__(128) bqsr_prep_kernel(GatherArgs A) {
 // base code of a BAM nibble: A C G T -> 0..3, everything else 8 (bit 3 = "not ACGT", bqsr.go:509)
 __device__ __forceinline__ uint32_t nib_code(uint32_t nib) { return (uint32_t)((0x8888888388828108ull >> (4 * nib)) & 0xfull); }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bqsr_count_kernel(GatherArgs A) {
+// rare per-base events of the lean path, out of line: QUAL without a shared-memory slot, QUAL > 93, base past the contig end
+__device__ __noinline__ void count_rare(const GatherArgs& A, int cov, int q, int cyc, uint32_t ctx, bool okc, uint32_t snp, bool past_end, uint32_t* errbits) {
+    if (q > 93) { *errbits |= DERR_QUAL_RANGE; return; }
+    if (past_end) { *errbits |= DERR_REFEND; return; }
+    atomicAdd(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_cycle(cyc)), 1ull);
+    if (okc) atomicAdd(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_ctx((int)ctx)), 1ull);
+    if (snp) {
+        atomicAdd(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_cycle(cyc)) + 1, 1ull);
+        if (okc) atomicAdd(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_ctx((int)ctx)) + 1, 1ull);
+    }
+}
+
+// shared memory through explicit 32-bit shared-window addresses (generic pointers cost an address conversion per access)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ int lds_s8(uint32_t a) { int v; asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void reds_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+struct LeanSmem { uint32_t obs, mis, refcode, qslot, nib; };   // shared-window byte addresses
+
+// Lean path: clipped CIGAR is a single M operation and every cycle is within --max-cycle (checked by the caller).
+// Everything loop-invariant is hoisted: per-lane byte pointers advance by constants, the neighbour base codes are software
+// pipelined (previous / current / next 32-base step) so the walk is always ascending, REV folds the strand selects away.
+template <bool REV>
+__device__ __forceinline__ void count_read_lean(const GatherArgs& A, const LeanSmem S, const uint32_t row_bytes, const uint32_t ctx_off_bytes, const int Lc,
+                                                const uint4 d0, const uint4 d1, const uint8_t* __restrict__ qualp, const uint8_t* __restrict__ seqp,
+                                                const uint8_t* __restrict__ ref, const int64_t reflen, const unsigned lane, uint32_t* errbits) {
+    const int L = (int)(d0.y >> 16), c_s0 = (int)(d0.y & 0xffff);
+    const uint32_t flags = d0.z & 0xff, cov = (d0.z >> 8) & 0xff, n_skip = (d0.z >> 16) & 0xff;
+    const int last = (flags & DF_LAST) ? 1 : 0;
+    const int64_t j0 = (int64_t)(int32_t)d0.x - 1;
+    const int nref = (int)max((int64_t)0, min((int64_t)L, reflen - j0));
+    const int nit = (L + 31) >> 5;
+    const int rof = 1 - 2 * last, inc = REV ? -rof : rof, cf = rof + (REV ? (L - 1) * rof : 0);   // prepareCycleCovariates, bqsr.go:376-383
+    // low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2
+    const uint8_t* qp = qualp + lane;
+    int leftPos = L, rightPos = -1;
+    {
+        const uint8_t* q2 = qp;
+        for (int it = 0, i = lane; it < nit; it++, i += 32, q2 += 32) {
+            const unsigned b = __ballot_sync(FULL_MASK, i < L && *q2 > 2);
+            if (b) { if (leftPos == L) leftPos = it * 32 + __ffs(b) - 1; rightPos = it * 32 + 31 - __clz(b); }
+        }
+    }
+    const int wlo = REV ? leftPos : leftPos + 1, whi = REV ? rightPos - 1 : rightPos;
+    const uint32_t wspan = (whi >= wlo) ? (uint32_t)(whi - wlo) : 0u;
+    const int wlo_eff = (whi >= wlo) ? wlo : 0x7fffffff;
+    const uint32_t nsh = ((uint32_t)(c_s0 + lane) & 1u) ? 0u : 4u;     // nibble of this lane's bases (32*it is even: same parity every step)
+    const uint8_t* sp = seqp + ((c_s0 + (int)lane) >> 1);
+    const uint8_t* rp = ref + j0 + lane;
+    const uint32_t obs0 = S.obs + cov * (uint32_t)A.n_slots * row_bytes, mis0 = S.mis + cov * (uint32_t)A.n_slots * row_bytes;
+    int cidx4 = (cf + (int)lane * inc + Lc) * 4;                      // byte offset of the cycle cell inside a row
+    const int cstep4 = 128 * inc;
+    uint32_t next_code = ((int)lane < L) ? lds_u8(S.nib + ((*sp >> nsh) & 15u)) : 8u;
+    uint32_t prev_edge = 8;
+    uint32_t skipbits = 0;
+    if (n_skip | (flags & DF_SKIP_OVF)) {
+        for (int it = 0, i = lane; it < nit; it++, i += 32) {
+            bool sk1 = false;
+            if (n_skip) {
+                const uint32_t sk[4] = {d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+                for (int r = 0; r < 4; r++) if (r < (int)n_skip) sk1 |= ((uint32_t)i >= (sk[r] & 0xffff)) & ((uint32_t)i <= (sk[r] >> 16));
+            } else sk1 = (i < L) && ((A.ovf_bits[(size_t)d0.w * OVF_WORDS + (i >> 5)] >> (i & 31)) & 1);
+            skipbits |= (sk1 ? 1u : 0u) << it;
+        }
+    }
+    int i = lane;
+#pragma unroll 1
+    for (int it = 0; it < nit; it++) {
+        const uint32_t code = next_code;
+        sp += 16;
+        next_code = (i + 32 < L) ? lds_u8(S.nib + ((*sp >> nsh) & 15u)) : 8u;
+        const uint32_t q = (i < L) ? (uint32_t)*qp : 0u;
+        const uint32_t rb = (i < nref) ? (uint32_t)*rp : 0xffu;
+        qp += 32; rp += 32;
+        uint32_t pcode;
+        if (REV) { pcode = __shfl_sync(FULL_MASK, code, (lane + 1) & 31); const uint32_t e = __shfl_sync(FULL_MASK, next_code, 0); if (lane == 31) pcode = e; }
+        else { pcode = __shfl_sync(FULL_MASK, code, (lane - 1) & 31); if (lane == 0) pcode = prev_edge; prev_edge = __shfl_sync(FULL_MASK, code, 31); }
+        const bool counted = (code < 8u) & (q >= 6u) & !((skipbits >> it) & 1u);      // bqsr.go:506-515 (code is 8 beyond L)
+        const int slot = (i < nref) ? lds_s8(S.qslot + q) : -1;                            // -1: no slot, QUAL > 93, or past the contig end
+        const uint32_t snp = lds_u8(S.refcode + rb) != code;
+        const bool okc = (pcode < 8u) & ((uint32_t)(i - wlo_eff) <= wspan);
+        const uint32_t ctx = REV ? ((pcode ^ 3u) | ((code ^ 3u) << 2)) : (pcode | (code << 2));   // key>>4 = prev | cur<<2 (bqsr.go:64-76)
+        if (counted) {
+            if (slot >= 0) {
+                const uint32_t orow = obs0 + (uint32_t)slot * row_bytes;
+                reds_inc(orow + (uint32_t)cidx4);
+                if (okc) reds_inc(orow + ctx_off_bytes + ctx * 4u);
+                if (snp) {   // mismatches are sparse (~0.5 % of bases)
+                    const uint32_t mrow = mis0 + (uint32_t)slot * row_bytes;
+                    reds_inc(mrow + (uint32_t)cidx4);
+                    if (okc) reds_inc(mrow + ctx_off_bytes + ctx * 4u);
+                }
+            } else count_rare(A, (int)cov, (int)q, (cidx4 >> 2) - Lc, ctx, okc, snp, i >= nref, errbits);
+        }
+        cidx4 += cstep4; i += 32;
+    }
+}
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2048 / (WARPS_PER_BLOCK * 32 * 2)) bqsr_count_kernel(GatherArgs A) {
     extern __shared__ uint32_t sm_tab[];
     __shared__ uint8_t sm_refcode[256];   // baseToIntMap (bqsr.go:247-252): A/a/* C/c G/g T/t -> 0..3, everything else 8
-    __shared__ int8_t sm_qslot[96];
+    __shared__ int8_t sm_qslot[256];      // QUAL -> shared-memory slot, -1 = none (and for QUAL > 93)
+    __shared__ uint8_t sm_nib[16];        // BAM nibble -> A C G T = 0..3, everything else 8
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
     const int cells = A.geom.n_cov * A.n_slots * A.ncols_s;
-    for (int i = threadIdx.x; i < cells; i += blockDim.x) sm_tab[i] = 0;
+    uint32_t* sm_mis = sm_tab + cells;
+    for (int i = threadIdx.x; i < 2 * cells; i += blockDim.x) sm_tab[i] = 0;
     {
         const int b = threadIdx.x; uint8_t c = 8;
         if (b == 'A' || b == 'a' || b == '*') c = 0; else if (b == 'C' || b == 'c') c = 1; else if (b == 'G' || b == 'g') c = 2; else if (b == 'T' || b == 't') c = 3;
         sm_refcode[b] = c;
-        if (b < 96) sm_qslot[b] = b < 94 ? A.qslot[b] : (int8_t)-1;
+        sm_qslot[b] = b < 94 ? A.qslot[b] : (int8_t)-1;
+        if (b < 16) sm_nib[b] = (uint8_t)nib_code((uint32_t)b);
     }
     __syncthreads();
     const int Lc = A.Lc, ncols_s = A.ncols_s, max_cycle = A.geom.max_cycle;
-    for (uint64_t k = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + w; k < A.n; k += (uint64_t)gridDim.x * WARPS_PER_BLOCK) {
+    LeanSmem LS;
+    LS.obs = (uint32_t)__cvta_generic_to_shared(sm_tab); LS.mis = (uint32_t)__cvta_generic_to_shared(sm_mis);
+    LS.refcode = (uint32_t)__cvta_generic_to_shared(sm_refcode); LS.qslot = (uint32_t)__cvta_generic_to_shared(sm_qslot); LS.nib = (uint32_t)__cvta_generic_to_shared(sm_nib);
+    // The per-read critical path is a chain of dependent DRAM accesses (descriptor -> offsets -> strips); with ~32 resident
+    // warps per SM that latency, not the instruction count, bounds the kernel.  So the chain is software pipelined across
+    // reads WITHOUT holding data in registers: while read k is processed, the scalars of read k+2W are requested and the
+    // cache lines of read k+W (QUAL, SEQ, reference window) are pulled into L1 with prefetch instructions.
+    const uint64_t stride = (uint64_t)gridDim.x * WARPS_PER_BLOCK;
+    uint64_t kk = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + w;
+    uint4 pd0 = make_uint4(0, 0, 0, 0); uint64_t pqo = 0, pso = 0; int32_t prid = 0;     // scalars of the NEXT read (k + W)
+    if (kk + stride < A.n) { pd0 = *reinterpret_cast<const uint4*>(A.desc + kk + stride); pqo = A.qual_off[kk + stride]; pso = A.seq_off[kk + stride]; prid = A.refid[kk + stride]; }
+    for (uint64_t k = kk; k < A.n; k += stride) {
+        // request the scalars of read k + 2W (consumed at the end of this iteration)
+        uint4 nd0 = make_uint4(0, 0, 0, 0); uint64_t nqo = 0, nso = 0; int32_t nrid = 0;
+        if (k + 2 * stride < A.n) { nd0 = *reinterpret_cast<const uint4*>(A.desc + k + 2 * stride); nqo = A.qual_off[k + 2 * stride]; nso = A.seq_off[k + 2 * stride]; nrid = A.refid[k + 2 * stride]; }
+        // pull the lines of read k + W towards L1: lanes 0..7 cover <= 8 lines (QUAL 3, SEQ 2, reference 3 for 192 bases)
+        {
+            const int pL = (int)(pd0.y >> 16), pc0 = (int)(pd0.y & 0xffff);
+            if (pL > 0) {
+                const uint8_t* pq = A.qual + pqo + pc0; const uint8_t* ps = A.seq + pso + (pc0 >> 1);
+                const uint8_t* pr = A.ref[prid] + ((int64_t)(int32_t)pd0.x - 1);
+                const uint8_t* ptr = nullptr;
+                if (lane < 3) { if ((int)lane * 128 < pL + 127) ptr = pq + lane * 128; }
+                else if (lane < 5) { if ((int)(lane - 3) * 128 < (pL >> 1) + 127) ptr = ps + (lane - 3) * 128; }
+                else if (lane < 8) { if ((int)(lane - 5) * 128 < pL + 127) ptr = pr + (lane - 5) * 128; }
+                if (ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
+            }
+        }
         // descriptor: two 16-byte loads, broadcast to the warp
         const uint4 d0 = *reinterpret_cast<const uint4*>(A.desc + k);
         const int L = (int)(d0.y >> 16);
-        if (L == 0) continue;
+        if (L == 0) { pd0 = nd0; pqo = nqo; pso = nso; prid = nrid; continue; }
         const uint4 d1 = *(reinterpret_cast<const uint4*>(A.desc + k) + 1);
         const int c_pos = (int)d0.x, c_s0 = (int)(d0.y & 0xffff);
         const uint32_t flags = d0.z & 0xff, cov = (d0.z >> 8) & 0xff, n_skip = (d0.z >> 16) & 0xff;
@@ -328,7 +459,21 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bqsr_count_kernel(Gather
         const uint8_t* qualp = A.qual + A.qual_off[k] + c_s0;
         const uint8_t* seqp = A.seq + A.seq_off[k];
         const uint8_t* ref = A.ref[refid]; const int64_t reflen = (int64_t)A.ref_len[refid];
+        pd0 = nd0; pqo = nqo; pso = nso; prid = nrid;     // (the `continue`s below must not skip this hand-over)
         const int nit = (L + 31) >> 5;
+        {
+            // common case: single M operation and all cycles within --max-cycle -> lean path
+            const int rof_ = 1 - 2 * last, ca = rof_ + reversed * (L - 1) * rof_, cb = ca + (L - 1) * (1 - 2 * reversed) * rof_;
+            if ((flags & DF_SINGLE_M) && max(ca, cb) <= max_cycle && min(ca, cb) >= -max_cycle) {
+                uint32_t eb = 0;
+                if (reversed) count_read_lean<true>(A, LS, (uint32_t)ncols_s * 4u, (uint32_t)(2 * Lc + 1) * 4u, Lc, d0, d1, qualp, seqp, ref, reflen, lane, &eb);
+                else count_read_lean<false>(A, LS, (uint32_t)ncols_s * 4u, (uint32_t)(2 * Lc + 1) * 4u, Lc, d0, d1, qualp, seqp, ref, reflen, lane, &eb);
+                eb = __reduce_or_sync(FULL_MASK, eb);
+                if (eb && lane == 0) atomicOr(A.err, eb);
+                continue;
+            }
+        }
+        // ---- general path: insertions / deletions, or a cycle beyond --max-cycle somewhere in the read ----
         // low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2
         int leftPos = L, rightPos = -1;
         for (int it = 0; it < nit; it++) {
@@ -395,23 +540,32 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bqsr_count_kernel(Gather
             const int cyc = cf + ic * inc;
             const bool badc = (cyc > max_cycle) | (cyc < -max_cycle);                     // checkCycleCovariate :364-369
             if (counted & badc) errbits |= DERR_CYCLE;
-            const uint32_t qq = q > 93 ? 93u : q;
-            const int slot = sm_qslot[qq];
+            const int slot = sm_qslot[q];
             const bool okc = counted & !(pcode & 8) & have_win & ((uint32_t)(ic - wlo) <= wspan);
             const uint32_t ctx = ((pcode ^ cmask) & 3u) | (((code ^ cmask) & 3u) << 2);   // key>>4 = prev | cur<<2 (bqsr.go:64-76), complemented for reverse reads
             if (counted && q <= 93 && !badc) {
                 if (slot >= 0) {
+#ifndef EXP_NO_OBS
                     const uint32_t row = (row0 + (uint32_t)slot) * (uint32_t)ncols_s;
                     atomicAdd(&sm_tab[row + (uint32_t)(cyc + Lc)], 1u);
                     if (okc) atomicAdd(&sm_tab[row + (uint32_t)(2 * Lc + 1) + ctx], 1u);
+#endif
                 } else {
                     atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_cycle(cyc)), 1ull);
                     if (okc) atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_ctx((int)ctx)), 1ull);
                 }
-                if (snp) {   // mismatches are rare: straight to the global table
-                    atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_cycle(cyc)) + 1, 1ull);
-                    if (okc) atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_ctx((int)ctx)) + 1, 1ull);
+#ifndef EXP_NO_MIS
+                if (snp) {
+                    if (slot >= 0) {   // mismatches are sparse (~0.5 % of bases): shared atomics on the CTA's second table
+                        const uint32_t row = (row0 + (uint32_t)slot) * (uint32_t)ncols_s;
+                        atomicAdd(&sm_mis[row + (uint32_t)(cyc + Lc)], 1u);
+                        if (okc) atomicAdd(&sm_mis[row + (uint32_t)(2 * Lc + 1) + ctx], 1u);
+                    } else {
+                        atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_cycle(cyc)) + 1, 1ull);
+                        if (okc) atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_ctx((int)ctx)) + 1, 1ull);
+                    }
                 }
+#endif
             }
         }
         errbits = __reduce_or_sync(FULL_MASK, errbits);
@@ -419,11 +573,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) bqsr_count_kernel(Gather
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
-        const uint32_t v = sm_tab[i];
-        if (!v) continue;
+        const uint32_t v = sm_tab[i], e = sm_mis[i];
+        if (!(v | e)) continue;
         const int col_s = i % ncols_s, cs = i / ncols_s, slot = cs % A.n_slots, cov = cs / A.n_slots;
         const int col_g = col_s < 2 * Lc + 1 ? A.geom.col_cycle(col_s - Lc) : A.geom.col_ctx(col_s - (2 * Lc + 1));
-        atomicAdd(A.tables + 2 * A.geom.idx(cov, A.slot_q[slot], col_g), (unsigned long long)v);
+        if (v) atomicAdd(A.tables + 2 * A.geom.idx(cov, A.slot_q[slot], col_g), (unsigned long long)v);
+        if (e) atomicAdd(A.tables + 2 * A.geom.idx(cov, A.slot_q[slot], col_g) + 1, (unsigned long long)e);
     }
 }
 
@@ -490,11 +645,11 @@ int phase_bqsr_gather(elp_ctx* c) {
             for (int q = 6; q < 94; q++) if (h[q]) qs.push_back(q);
             std::sort(qs.begin(), qs.end(), [&](int a, int b) { return h[a] != h[b] ? h[a] > h[b] : a < b; });
             const size_t per_slot = (size_t)std::max(1, c->geom.n_cov) * A.ncols_s * 4;
-            const int max_slots = (int)std::min<size_t>(94, (48 * 1024) / per_slot);
+            const int max_slots = (int)std::min<size_t>(94, (48 * 1024) / (2 * per_slot));   // observation + mismatch tables
             A.n_slots = std::min<int>((int)qs.size(), max_slots);
             for (int s = 0; s < A.n_slots; s++) { A.qslot[qs[s]] = (int8_t)s; A.slot_q[s] = (uint8_t)qs[s]; }
         }
-        const size_t smem = (size_t)c->geom.n_cov * A.n_slots * A.ncols_s * 4;
+        const size_t smem = (size_t)c->geom.n_cov * A.n_slots * A.ncols_s * 4 * 2;
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         // descriptors (32 B/read) and the overflow skip bitmasks live in scratch buffers that are free in this phase
         CUDA_TRY(c, c->keys_a.reserve(n * 4 + 8, c->stream));

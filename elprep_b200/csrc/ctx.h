@@ -122,6 +122,7 @@ struct elp_ctx {
     bool gathered = false, finalized = false;
     uint8_t* d_lut = nullptr;                 // [n_cov][94][2*lut_maxcyc+1][17]
     int lut_maxcyc = 0;
+    size_t lut_cap = 0;
     uint8_t* d_cov_exists = nullptr;          // [n_cov]
 
     // ---- measurement ----
