@@ -50,6 +50,7 @@ class Context:
             raise ElprepError(rc, (self.L.elp_last_error(None) or b"").decode())
         self.h = h
         self._keep = (names, ids, lbs, pus, sq)
+        self._keep_opts = dict(quantize_levels=quantize_levels, sqq=list(sqq) if sqq is not None else None)
 
     def close(self):
         if getattr(self, "h", None):

@@ -178,3 +178,29 @@ def test_invalid_qual_is_an_error():
         ctx.sort_markdup()
     assert ei.value.code == -10 and "Invalid QUAL character" in str(ei.value)
     ctx.close()
+
+
+def test_reference_style_api():
+    """the phase order of runBestPracticesPipelineIntermediateSam (cmd/filter.go:142-211) through the mirrored operator API"""
+    import os
+    import tempfile
+    from elprep_b200 import filters
+    w = synth.make_workload(6_000, SMALL, seed=41)
+    n = w.batch.n
+    batches = [w.batch.take(np.arange(a, b)) for a, b in ((0, n // 2), (n // 2, n))]
+    reads = filters.DeviceSam()
+    md, fragments, pairs = filters.MarkDuplicates(False)
+    filters.InputBatches(w.header, batches).RunPipeline(reads, [filters.AddREFID, md], sam.Coordinate)      # phase 1
+    assert w.header.HDSO() == sam.Coordinate
+    recal = filters.NewBaseRecalibrator(w.sites, w.contig_bases)
+    tables = recal.Recalibrate(reads, 500)                                                                  # phase 3
+    with tempfile.TemporaryDirectory() as d:
+        tables.FinalizeBQSRTables()
+        tables.PrintBQSRTables(os.path.join(d, "x.recal"))                                                  # phase 4
+        report = open(os.path.join(d, "x.recal")).read()
+    reads.RunPipeline(reads, [tables.ApplyBQSR(0, [], 500)], sam.Keep)                                      # phase 5
+    out = filters.HostResult()
+    reads.RunPipeline(out, [], sam.Keep)                                                                    # phase 6
+    o = oracle_pipeline(w)
+    assert np.array_equal(out.record_index, o["perm"]) and np.array_equal(out.flag, o["flag"])
+    assert np.array_equal(out.qual[:int(out.qual_off[-1])], o["qual"]) and report == o["report"]

@@ -1,0 +1,43 @@
+"""CPU tests of the host-side mirror of the reference's operator API (composition, sorting-order logic, multi-rank partition)."""
+import numpy as np
+
+from elprep_b200 import filters, sam
+
+
+def test_compose_filters_skips_nil():
+    h = sam.Header(sq=[{"SN": "c", "LN": 10}])
+    calls = []
+    f1 = lambda hdr: None                                   # a Filter may return nil (sam/filter-pipeline.go:39-40,166-170)
+    f2 = lambda hdr: (lambda b: calls.append("f2") or b)
+    out = filters.compose_filters(h, [f1, None, f2])
+    assert len(out) == 1 and out[0]("x") == "x" and calls == ["f2"]
+
+
+def test_effective_sorting_order():
+    h = sam.Header(sq=[{"SN": "c", "LN": 10}], so=sam.Coordinate)
+    assert filters.effective_sorting_order(sam.Coordinate, h, sam.Coordinate) == sam.Keep          # already sorted: skip (:214-217)
+    h = sam.Header(sq=[{"SN": "c", "LN": 10}], so=sam.Unsorted)
+    assert filters.effective_sorting_order(sam.Coordinate, h, sam.Unsorted) == sam.Coordinate and h.HDSO() == sam.Coordinate
+    h = sam.Header(sq=[{"SN": "c", "LN": 10}], so=sam.Queryname)
+    assert filters.effective_sorting_order(sam.Keep, h, sam.Queryname) == sam.Keep                 # Keep -> original order, unchanged
+
+
+def test_markduplicates_needs_rg_id():
+    h = sam.Header(sq=[{"SN": "c", "LN": 10}], rg=[{"LB": "x"}])
+    md, _, _ = filters.MarkDuplicates(False)
+    try:
+        md(h)
+        assert False
+    except ValueError as e:
+        assert "Missing mandatory ID entry" in str(e)        # filters/mark-duplicates.go:419
+
+
+def test_header_tables():
+    h = sam.Header(sq=[{"SN": "a", "LN": 5}, {"SN": "b", "LN": 7}], rg=[{"ID": "r1", "LB": "L", "PU": "p"}, {"ID": "r2", "LB": "L"}, {"ID": "r3"}, {"ID": "r4", "PU": "p"}])
+    lib, names = h.rg_lib_ids()
+    assert lib.tolist() == [0, 0, -1, -1] and names == ["L"]
+    cov, cn = h.rg_cov_ids()
+    assert cov.tolist() == [0, 1, 2, 0] and cn == ["p", "r2", "r3"]                                # PU if present else ID (bqsr.go:35-51)
+    assert h.refid_table() == {"*": -1, "a": 0, "b": 1}
+    b = sam.AlignmentBatch.from_records(h, [dict(QNAME="q", RNAME="b", RNEXT="=", POS=3, CIGAR="2M1M", SEQ="ACG", QUAL=[1, 2, 3], RG="r2")])
+    assert b.refid[0] == 1 and b.nref[0] == 1 and sam.decode_cigar(b.cigar) == "3M"               # adjacent identical ops merge (sam-types.go:708-710)

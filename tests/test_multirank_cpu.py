@@ -1,0 +1,78 @@
+"""world_size-2 (gloo, CPU) test of the multi-GPU partitioning logic: contig groups (sfm-style, sam/split-merge.go:178-213),
+local sort + markdup + gather per rank, ONE all_reduce(sum) of the integer BQSR tables (the summation of
+LoadAndCombineBQSRTables, filters/print-bqsr.go:310-329), and concatenation of the groups as the global order."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+    import bench
+    import oracle
+    from elprep_b200 import synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    contigs = [("c1", 300_000), ("c2", 250_000), ("c3", 120_000), ("c4", 80_000)]
+    w = synth.make_workload(6000, contigs, seed=77, cross_contig_frac=0.0, threads=2)
+    groups = bench.contig_groups(contigs, world)
+    mine = {n for n, _ in groups[rank]}
+    names = [n for n, _ in contigs]
+    own = np.array([names[r] in mine if r >= 0 else (rank == world - 1) for r in w.batch.refid])     # unmapped reads go to the last rank
+    sub = w.batch.take(np.nonzero(own)[0])
+    oracle.mark_duplicates(sub, w.header, n_threads=1)
+    perm = oracle.coordinate_sort(sub, n_threads=1)
+    srt = sub.take(perm)
+    ref = oracle.Reference(w.header, w.contig_bases, w.sites)
+    t = oracle.bqsr_gather(srt, w.header, ref)
+    tabs = [torch.from_numpy(a) for a in (t.q_obs, t.q_mis, t.c_obs, t.c_mis, t.x_obs, t.x_mis)]
+    for x in tabs:
+        dist.all_reduce(x)                                   # the single collective of the path
+    np.save(os.path.join(out_dir, f"flags_{rank}.npy"), np.stack([np.nonzero(own)[0][perm], srt.flag.astype(np.int64)]))
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "tables.npz"), *[x.numpy() for x in tabs])
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_contig_groups_balance():
+    sys.path.insert(0, ROOT)
+    import bench
+    from elprep_b200 import synth
+    for n in (1, 2, 4, 8):
+        g = bench.contig_groups(synth.HG38, n)
+        loads = [sum(l for _, l in x) for x in g]
+        assert sorted(c for x in g for c, _ in x) == sorted(c for c, _ in synth.HG38)
+        assert max(loads) <= 1.15 * (sum(loads) / n) or n == 8 and max(loads) <= 1.3 * (sum(loads) / n)
+
+
+def test_two_rank_partition_equals_whole(tmp_path):
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    import oracle
+    from elprep_b200 import synth
+    port = 29600 + (os.getpid() % 300)
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    contigs = [("c1", 300_000), ("c2", 250_000), ("c3", 120_000), ("c4", 80_000)]
+    w = synth.make_workload(6000, contigs, seed=77, cross_contig_frac=0.0, threads=2)
+    b = w.batch.copy()
+    oracle.mark_duplicates(b, w.header, n_threads=1)
+    perm = oracle.coordinate_sort(b, n_threads=1)
+    srt = b.take(perm)
+    t = oracle.bqsr_gather(srt, w.header, oracle.Reference(w.header, w.contig_bases, w.sites))
+    z = np.load(os.path.join(tmp_path, "tables.npz"))
+    for got, exp in zip([z[k] for k in z.files], (t.q_obs, t.q_mis, t.c_obs, t.c_mis, t.x_obs, t.x_mis)):
+        assert np.array_equal(got, exp), "summed per-rank tables differ from the whole-genome tables"
+    # duplicate flags: every read gets the same FLAG as in the whole run; per-rank orders are sub-sequences of the global order
+    whole = dict(zip(perm.tolist(), srt.flag.tolist()))
+    for r in range(2):
+        idx, fl = np.load(os.path.join(tmp_path, f"flags_{r}.npy"))
+        assert all(whole[int(i)] == int(f) for i, f in zip(idx, fl))
+        pos_in_whole = {int(v): k for k, v in enumerate(perm)}
+        ranks = [pos_in_whole[int(i)] for i in idx]
+        assert ranks == sorted(ranks)
