@@ -129,17 +129,17 @@ def main():
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     from elprep_b200 import synth
-    all_contigs = synth.scaled_hg38(GENOME_SCALE)
+    all_contigs = synth.scaled_hg38(GENOME_SCALE / world)     # weak scaling: the genome grows with the number of GPUs, ~155 Mbp (29x coverage) per contig group
     groups = contig_groups(all_contigs, world)
     contigs = groups[rank]
     threads = min(os.cpu_count() or 1, 64)
-    workload_name = f"hg38/{GENOME_SCALE:g}-shaped contig group, {args.reads} synthetic 150-bp paired reads per GPU, sort+markdup+BQSR(gather,finalize,apply)"
+    workload_name = f"hg38/{GENOME_SCALE / world:g}-shaped genome split into {world} contig group(s), {args.reads} synthetic 150-bp paired reads per GPU, sort+markdup+BQSR(gather,finalize,apply)"
 
     if args.impl == "reference":
         if rank != 0:
             return
         n_sample = min(args.cpu_sample, args.reads)
-        w = synth.make_workload(n_sample // 2, contigs, seed=20260924, threads=threads)
+        w = synth.make_workload(args.reads // 2, contigs, seed=20260924, threads=threads)   # the same workload as our arm; each step processes its first n_sample reads
         times = []
         for i in range(args.warmup + args.steps):
             n, t = cpu_pipeline(w, n_sample, threads)

@@ -75,6 +75,15 @@ __device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ void st_relaxed_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // set FLAG bits on a u16 column from concurrent threads (two reads share one 32-bit word)
 __device__ __forceinline__ void atomic_or_u16(uint16_t* col, uint64_t i, uint16_t bits) {
     uint32_t* w = reinterpret_cast<uint32_t*>(col) + (i >> 1);

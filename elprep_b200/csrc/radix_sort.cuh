@@ -164,19 +164,38 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K*
         // chained scan across tiles (decoupled look-back), one thread per digit
         uint32_t excl = 0;
         uint32_t* my = status + (uint64_t)tile * RADIX + tid;
+        // flag and value travel in ONE 32-bit word, so relaxed accesses are enough (no other data is published through it).
+        // The walk back over predecessor tiles issues LB independent loads per step: with hundreds of tiles in flight a
+        // one-load-at-a-time walk is a chain of serialized L2 round trips and caps the whole pass.
         if (tile > 0) {
-            st_release_u32(my, total | ST_PARTIAL);
+            st_relaxed_u32(my, total | ST_PARTIAL);
+#ifndef RS_LB
+#define RS_LB 8
+#endif
+            constexpr int LB = RS_LB;
             int64_t t = (int64_t)tile - 1;
-            for (;;) {
-                uint32_t s = ld_acquire_u32(status + (uint64_t)t * RADIX + tid);
-                uint32_t f = s >> 30;
-                if (f == 0) continue;
-                excl += s & ST_VALMASK;
-                if (f == 2) break;
-                t--;
+            bool done = false;
+            while (!done) {
+                uint32_t sv[LB];
+#pragma unroll
+                for (int j = 0; j < LB; j++) sv[j] = (t - j >= 0) ? ld_relaxed_u32(status + (uint64_t)(t - j) * RADIX + tid) : ST_INCLUSIVE;
+#pragma unroll
+                for (int j = 0; j < LB; j++) {
+                    if (done) break;
+                    uint32_t s = sv[j];
+                    while ((s >> 30) == 0) {   // predecessor not published yet
+#ifdef RS_NANOSLEEP
+                        __nanosleep(RS_NANOSLEEP);
+#endif
+                        s = ld_relaxed_u32(status + (uint64_t)(t - j) * RADIX + tid);
+                    }
+                    excl += s & ST_VALMASK;
+                    if ((s >> 30) == 2) done = true;
+                }
+                t -= LB;
             }
         }
-        st_release_u32(my, ((excl + total) & ST_VALMASK) | ST_INCLUSIVE);
+        st_relaxed_u32(my, ((excl + total) & ST_VALMASK) | ST_INCLUSIVE);
         gbase[tid] = gofs[tid] + excl - dstart;   // modulo 2^32: final index = gbase[d] + tile-local sorted position
     }
     __syncthreads();
@@ -223,7 +242,12 @@ struct Workspace {
 };
 
 template <class K> struct Cfg;
-template <> struct Cfg<K64> { static constexpr int THREADS = 256, ITEMS = 12, MIN_CTAS = 4; };
+#ifndef RS64_THREADS
+#define RS64_THREADS 256
+#define RS64_ITEMS 12
+#define RS64_MINCTAS 4
+#endif
+template <> struct Cfg<K64> { static constexpr int THREADS = RS64_THREADS, ITEMS = RS64_ITEMS, MIN_CTAS = RS64_MINCTAS; };
 template <> struct Cfg<K128> { static constexpr int THREADS = 256, ITEMS = 8, MIN_CTAS = 4; };
 
 template <class K> inline size_t tile_size() { return (size_t)Cfg<K>::THREADS * Cfg<K>::ITEMS; }
