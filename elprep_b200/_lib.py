@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("ELPREP_B200_LIB", os.path.join(_HERE, "lib", "libelprep_b200.so"))   # override: kernel-ablation builds (tools/ablate.sh)
 
 SO_KEEP, SO_UNKNOWN, SO_UNSORTED, SO_QUERYNAME, SO_COORDINATE = 0, 1, 2, 3, 4
+MARKDUP, MARKDUP_OPTICAL = 1, 2
 
 
 class ElpConfig(C.Structure):
@@ -25,6 +26,13 @@ class ElpBatch(C.Structure):
                 ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "l_seq", "seq", "qual")]
 
 
+class ElpDupMetrics(C.Structure):
+    COUNTERS = ("unpaired_reads_examined", "read_pairs_examined", "secondary_or_supplementary_reads", "unmapped_reads",
+                "unpaired_read_duplicates", "read_pair_duplicates", "read_pair_optical_duplicates")
+    _fields_ = [(k, C.c_int64) for k in COUNTERS] + [("estimated_library_size", C.c_int64), ("percent_duplication", C.c_double),
+                                                      ("roi", C.c_double * 100), ("has_roi", C.c_int32)]
+
+
 class ElpKernelStat(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("launches", C.c_uint64), ("ms", C.c_double), ("alg_bytes", C.c_double)]
 
@@ -33,7 +41,9 @@ EXPORTS = ["elp_create", "elp_destroy", "elp_last_error", "elp_reserve", "elp_re
            "elp_append_batch", "elp_n_reads", "elp_sort_markdup", "elp_bqsr_gather", "elp_bqsr_tables_len", "elp_bqsr_n_cov",
            "elp_bqsr_cov_name", "elp_bqsr_tables_get", "elp_bqsr_tables_put", "elp_bqsr_tables_device", "elp_bqsr_finalize",
            "elp_bqsr_empirical_get", "elp_bqsr_apply", "elp_fetch", "elp_fetch_qual_bytes", "elp_debug_adapt", "elp_launch_count",
-           "elp_kernel_stats", "elp_synchronize", "elp_reset_stats", "elp_timer_start", "elp_timer_stop", "elp_debug_sort_u64", "elp_debug_sort_u128"]
+           "elp_kernel_stats", "elp_synchronize", "elp_reset_stats", "elp_timer_start", "elp_timer_stop", "elp_debug_sort_u64", "elp_debug_sort_u128",
+           "elp_optical_n_libraries", "elp_optical_library_name", "elp_optical_metrics", "elp_optical_histogram", "elp_optical_merge",
+           "elp_print_duplicates_metrics"]
 
 _lib = None
 
@@ -85,5 +95,13 @@ def load():
     L.elp_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.elp_debug_sort_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
     L.elp_debug_sort_u128.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]
+    L.elp_optical_n_libraries.argtypes = [C.c_void_p]
+    L.elp_optical_library_name.restype = C.c_char_p
+    L.elp_optical_library_name.argtypes = [C.c_void_p, C.c_int32]
+    L.elp_optical_metrics.argtypes = [C.c_void_p, C.c_int32, C.POINTER(ElpDupMetrics)]
+    L.elp_optical_histogram.restype = C.c_int64
+    L.elp_optical_histogram.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+    L.elp_optical_merge.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+    L.elp_print_duplicates_metrics.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
     _lib = L
     return L

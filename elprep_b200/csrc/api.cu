@@ -85,7 +85,7 @@ int elp_create(const elp_config* cfg, elp_ctx** out) {
     for (int i = 0; i < c->n_rg; i++) {
         if (!cfg->rg_id || !cfg->rg_id[i]) { c->err = "Missing mandatory ID entry in an @RG line in a SAM file header."; return bail(ELP_EINVAL); }
         const char* lb = cfg->rg_lb ? cfg->rg_lb[i] : nullptr;
-        if (lb) { auto it = libs.find(lb); if (it == libs.end()) it = libs.emplace(lb, (int)libs.size()).first; c->rg_lib.push_back(it->second); } else c->rg_lib.push_back(-1);
+        if (lb) { auto it = libs.find(lb); if (it == libs.end()) { it = libs.emplace(lb, (int)libs.size()).first; c->lib_names.push_back(lb); } c->rg_lib.push_back(it->second); } else c->rg_lib.push_back(-1);
         const char* pu = cfg->rg_pu ? cfg->rg_pu[i] : nullptr;
         std::string name = pu ? pu : cfg->rg_id[i];
         auto it = covs.find(name);
@@ -124,7 +124,7 @@ void elp_destroy(elp_ctx* c) {
     for (auto p : c->d_ref) if (p) cudaFree(p);
     for (auto p : c->d_sites) if (p) cudaFree(p);
     void* singles[] = {c->d_rg_lib, c->d_rg_cov, c->d_contig_len, c->d_ranges, c->d_err, (void*)c->d_ref_ptrs, c->d_ref_len, (void*)c->d_site_ptrs, c->d_n_sites, c->d_tables,
-                       c->d_lut, c->d_cov_exists, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
+                       c->d_lut, c->d_cov_exists, c->d_opt_ctr, c->d_opt_hist, c->d_opt_ovf, c->d_opt_small, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
     for (void* p : singles) if (p) cudaFree(p);
     c->refid.release(); c->pos.release(); c->nref.release(); c->pnext.release(); c->tlen.release(); c->rg.release(); c->flag.release(); c->mapq.release();
     c->qname_off.release(); c->cigar_off.release(); c->qual_off.release(); c->seq_off.release(); c->qname.release(); c->seq.release(); c->qual.release(); c->cigar.release();
@@ -144,7 +144,7 @@ int elp_reset(elp_ctx* c) {
     cudaSetDevice(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->n = c->n_qname = c->n_cigar = c->n_qual = c->n_seq = 0;
-    c->adapted = c->sorted = c->qual_out_valid = c->gathered = c->finalized = false;
+    c->adapted = c->sorted = c->qual_out_valid = c->gathered = c->finalized = c->opt_valid = false;
     c->launches = 0;
     CUDA_TRY(c, cudaMemsetAsync(c->d_err, 0, 4, c->stream));
     return ELP_OK;
@@ -258,7 +258,8 @@ int elp_sort_markdup(elp_ctx* c, int sorting_order, int mark_duplicates) {
     cudaSetDevice(c->device);
     if (c->sorted) return c->fail(E_STATE, "elp_sort_markdup called twice (call elp_reset first)");
     if (sorting_order == ELP_SO_QUERYNAME) return c->fail(E_INVAL, "queryname order is not on the device path");
-    if (mark_duplicates) TRY(phase_markdup(c));
+    if (mark_duplicates != 0 && mark_duplicates != ELP_MARKDUP && mark_duplicates != ELP_MARKDUP_OPTICAL) return c->fail(E_INVAL, "elp_sort_markdup: mark_duplicates must be 0, ELP_MARKDUP or ELP_MARKDUP_OPTICAL");
+    if (mark_duplicates) TRY(phase_markdup(c, mark_duplicates == ELP_MARKDUP_OPTICAL));
     TRY(phase_coordinate_sort(c, sorting_order == ELP_SO_COORDINATE));
     return ELP_OK;
 }

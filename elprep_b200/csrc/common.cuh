@@ -20,6 +20,7 @@
 #define E_CLIP (-13)
 #define E_REFEND (-14)
 #define E_LIMIT (-15)
+#define E_TILE (-17)
 #define E_STATE (-16)
 
 // device-side error word bits (one u32 in global memory, OR-ed by kernels, read by the host after the phase)
@@ -31,6 +32,8 @@
 #define DERR_CIGAR_LIMIT 0x20u
 #define DERR_QUAL_RANGE 0x40u
 #define DERR_READLEN_LIMIT 0x80u
+#define DERR_TILE 0x100u         // QNAME tile/x/y field that strconv.ParseInt rejects (mark-optical-duplicates.go:57-64)
+#define DERR_TILE_RANGE 0x200u   // tile/x/y outside int32
 
 // FLAG bits (sam/sam-types.go:485-520)
 #define F_MULTIPLE 0x1

@@ -30,6 +30,13 @@ template <class T> struct DBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// duplication metrics of one library (filters.DuplicatesCtr, mark-optical-duplicates.go:95-110): the seven counters in the
+// reference's field order and the three count histograms (all, non-optical, optical)
+struct DupCounters { int64_t ctr[7] = {0, 0, 0, 0, 0, 0, 0}; std::map<int64_t, int64_t> hist[3]; };
+#define OPT_NCTR 8
+#define OPT_HBINS 1024
+#define OPT_OVF_CAP (1 << 16)
+
 struct KernelStat { uint64_t launches = 0; double ms = 0, alg_bytes = 0; };
 struct PendingEvent { std::string name; cudaEvent_t a, b; double alg_bytes; };
 
@@ -58,6 +65,7 @@ struct elp_ctx {
     std::vector<int32_t> rg_lib, rg_cov;       // per @RG
     int n_lib = 0;
     std::vector<std::string> cov_names;
+    std::vector<std::string> lib_names;       // [n_lib]
     int max_cycle = 500, quantize_levels = 0, optical_pixel_distance = 100;
     std::vector<uint8_t> sqq;
     std::string prefix = "GATK";
@@ -125,6 +133,11 @@ struct elp_ctx {
     size_t lut_cap = 0;
     uint8_t* d_cov_exists = nullptr;          // [n_cov]
 
+    // ---- duplication metrics (optical.cu) ----
+    void* d_opt_ctr = nullptr; void* d_opt_hist = nullptr; void* d_opt_ovf = nullptr; uint32_t* d_opt_small = nullptr;
+    std::vector<DupCounters> opt;             // [n_lib + 1], slot 0 = "Unknown Library"
+    bool opt_valid = false;
+
     // ---- measurement ----
     uint64_t launches = 0;
     std::map<std::string, KernelStat> stats;
@@ -180,7 +193,8 @@ int radix_sort_u128(elp_ctx* c, uint64_t* keys_a, uint64_t* keys_b, uint32_t* va
 int exclusive_scan_u32_to_u64(elp_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n);   // out[n+1]
 int exclusive_scan_u64(elp_ctx* c, const uint64_t* in, uint64_t* out, uint64_t n, uint64_t base);          // out[n+1], out[0]=base
 int phase_adapt(elp_ctx* c);
-int phase_markdup(elp_ctx* c);
+int phase_markdup(elp_ctx* c, bool optical);
+int phase_optical(elp_ctx* c, uint64_t npairs, const uint64_t* sorted_keys, const uint32_t* sorted_vals, int bS);
 int phase_coordinate_sort(elp_ctx* c, bool sort);
 int phase_bqsr_gather(elp_ctx* c);
 int phase_bqsr_finalize(elp_ctx* c, const char* report_path);

@@ -316,6 +316,8 @@ int check_device_errors(elp_ctx* c) {
     if (e & DERR_REFEND) return c->fail(E_REFEND, "a recalibrated read extends past the end of its reference sequence");
     if (e & DERR_CIGAR_LIMIT) return c->fail(E_LIMIT, "BQSR: CIGAR with more operations than the device kernel supports");
     if (e & DERR_QUAL_RANGE) return c->fail(E_LIMIT, "value outside the supported range (negative POS, or QUAL > 93 in a recalibrated read)");
+    if (e & DERR_TILE) return c->fail(E_TILE, "strconv.ParseInt: parsing a tile/x/y field of a QNAME: invalid syntax or value out of range");
+    if (e & DERR_TILE_RANGE) return c->fail(E_LIMIT, "optical duplicates: tile/x/y value outside int32");
     if (e & DERR_READLEN_LIMIT) return c->fail(E_LIMIT, "BQSR: read longer than the device kernel supports");
     return c->fail(E_CUDA, "unknown device error word 0x%x", e);
 }
@@ -346,11 +348,11 @@ int phase_adapt(elp_ctx* c) {
     return E_OK;
 }
 
-int phase_markdup(elp_ctx* c) {
+int phase_markdup(elp_ctx* c, bool optical) {
     int rc = phase_adapt(c);
     if (rc) return rc;
     const uint64_t n = c->n;
-    if (n == 0 || c->h_ranges.n_entering == 0) return E_OK;
+    if (n == 0 || c->h_ranges.n_entering == 0) return optical ? phase_optical(c, 0, nullptr, nullptr, 0) : E_OK;
     const DeviceRanges& R = c->h_ranges;
     CUDA_TRY(c, c->keys_a.reserve(2 * n + 4, c->stream)); CUDA_TRY(c, c->keys_b.reserve(2 * n + 4, c->stream));
     CUDA_TRY(c, c->vals_a.reserve(n + 4, c->stream)); CUDA_TRY(c, c->vals_b.reserve(n + 4, c->stream));
@@ -396,7 +398,7 @@ int phase_markdup(elp_ctx* c) {
         uint64_t npairs = 0;
         CUDA_TRY(c, cudaMemcpyAsync(&npairs, slot + n, 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        if (npairs >= 2) {
+        if (npairs >= (optical ? 1u : 2u)) {
             CUDA_TRY(c, c->pair_a.reserve(npairs + 4, c->stream)); CUDA_TRY(c, c->pair_b.reserve(npairs + 4, c->stream));
             PairLayout L{}; L.bS = bits_for((uint64_t)R.score_max * 2); L.bU = bU; L.bR = bR; L.bL = bL; L.upos_min = R.upos_min; L.score_max = R.score_max * 2;
             L.key_bits = L.bS + 2 * L.bU + 2 + 2 * L.bR + L.bL;
@@ -414,7 +416,8 @@ int phase_markdup(elp_ctx* c) {
             pair_mark_kernel<<<nblk(npairs, 256), 256, 0, c->stream>>>(npairs, in_b ? kb2 : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, L.bS, c->pair_a.p, c->pair_b.p,
                                                                       c->qname_off.p, c->qname.p, c->flag.p);
             c->end(); LAUNCH_CHECK(c);
+            if (optical) return phase_optical(c, npairs, in_b ? kb2 : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, L.bS);
         }
     }
-    return E_OK;
+    return optical ? phase_optical(c, 0, nullptr, nullptr, 0) : E_OK;
 }

@@ -96,7 +96,48 @@ class Context:
         return int(self.L.elp_n_reads(self.h))
 
     def sort_markdup(self, sorting_order=SO_COORDINATE, mark_duplicates=True):
+        """mark_duplicates: False/0, True/1 (MarkDuplicates(false)) or 2 (= _lib.MARKDUP_OPTICAL: also the duplication metrics)"""
         self._ck(self.L.elp_sort_markdup(self.h, sorting_order, int(mark_duplicates)))
+
+    # ---- duplication metrics (filters.MarkOpticalDuplicates) ----
+    def optical_libraries(self):
+        return [self.L.elp_optical_library_name(self.h, i).decode() for i in range(int(self.L.elp_optical_n_libraries(self.h)))]
+
+    def optical_metrics(self):
+        """-> list over slots of dict(counters..., estimated_library_size, percent_duplication, roi, hist=[{key: count}] * 3)"""
+        out = []
+        for slot in range(int(self.L.elp_optical_n_libraries(self.h))):
+            m = _lib.ElpDupMetrics()
+            self._ck(self.L.elp_optical_metrics(self.h, slot, C.byref(m)))
+            d = {k: int(getattr(m, k)) for k in _lib.ElpDupMetrics.COUNTERS}
+            d["estimated_library_size"] = int(m.estimated_library_size)
+            d["percent_duplication"] = float(m.percent_duplication)
+            d["roi"] = list(m.roi) if m.has_roi else None
+            hs = []
+            for which in range(3):
+                n = int(self.L.elp_optical_histogram(self.h, slot, which, None, None, 0))
+                if n < 0:
+                    raise ElprepError(-1, "elp_optical_histogram failed")
+                keys, cnt = np.zeros(n, np.int64), np.zeros(n, np.int64)
+                self.L.elp_optical_histogram(self.h, slot, which, _vp(keys), _vp(cnt), n)
+                hs.append({int(k): int(v) for k, v in zip(keys, cnt)})
+            d["hist"] = hs
+            out.append(d)
+        return out
+
+    def optical_merge(self, slot, counters=None, hist=None):
+        """add another worker's numbers (mergeDuplicatesCtrMaps): counters = 7 ints in DuplicatesCtr order, hist = 3 dicts"""
+        c7 = np.ascontiguousarray(counters, dtype=np.int64) if counters is not None else None
+        if c7 is not None:
+            self._ck(self.L.elp_optical_merge(self.h, slot, _vp(c7), 0, None, None, 0))
+        for which, h in enumerate(hist or []):
+            keys = np.array(sorted(h), dtype=np.int64)
+            cnt = np.array([h[k] for k in sorted(h)], dtype=np.int64)
+            if keys.size:
+                self._ck(self.L.elp_optical_merge(self.h, slot, None, which, _vp(keys), _vp(cnt), keys.size))
+
+    def print_duplicates_metrics(self, path, command_line="", started_on=""):
+        self._ck(self.L.elp_print_duplicates_metrics(self.h, path.encode(), command_line.encode(), started_on.encode()))
 
     def bqsr_gather(self):
         self._ck(self.L.elp_bqsr_gather(self.h))

@@ -58,6 +58,20 @@ def MarkDuplicates(alsoOpticals):
     return flt, fragments, pairs
 
 
+def MarkOpticalDuplicates(reads, pairs, opticalPixelDistance):
+    """filters.MarkOpticalDuplicates (filters/mark-optical-duplicates.go:468-517) -> map[library]*DuplicatesCtr.
+    The counting ran on the device inside the Finalize of phase 1 (MarkDuplicates(True)); this returns its result."""
+    if opticalPixelDistance != reads._opts["optical_pixel_distance"]:
+        raise ValueError("opticalPixelDistance differs from the context's --optical-duplicates-pixel-distance")
+    names = reads.ctx.optical_libraries()
+    return dict(zip(names, reads.ctx.optical_metrics()))
+
+
+def PrintDuplicatesMetrics(reads, metrics, commandLine, startedOn=""):
+    """filters.PrintDuplicatesMetrics (filters/mark-optical-duplicates.go:601-699); libraries in ascending name order."""
+    reads.ctx.print_duplicates_metrics(metrics, commandLine, startedOn)
+
+
 def compose_filters(header, hdr_filters):
     """sam.ComposeFilters (sam/filter-pipeline.go:163-198): call each Filter with the header, keep the non-nil results."""
     out = []
@@ -87,10 +101,11 @@ def effective_sorting_order(sorting_order, header, original):
 class DeviceSam:
     """The device-resident analogue of ``*sam.Sam``: implements both PipelineOutput (AddNodes) and PipelineInput (RunPipeline)."""
 
-    def __init__(self, device_ordinal=0, max_cycle=500, quantize_levels=0, sqq=None, prefix="GATK", profile=False):
+    def __init__(self, device_ordinal=0, max_cycle=500, quantize_levels=0, sqq=None, prefix="GATK", profile=False, optical_pixel_distance=100):
         self.Header = None
         self.ctx = None
-        self._opts = dict(device=device_ordinal, max_cycle=max_cycle, quantize_levels=quantize_levels, sqq=sqq, prefix=prefix, profile=profile)
+        self._opts = dict(device=device_ordinal, max_cycle=max_cycle, quantize_levels=quantize_levels, sqq=sqq, prefix=prefix, profile=profile,
+                          optical_pixel_distance=optical_pixel_distance)
         self._markdup = False
         self._batches = []       # host copies in arrival order (the Go side keeps []*Alignment and gets indices back)
 
@@ -108,7 +123,8 @@ class DeviceSam:
             self._batches.append(b)
             self.ctx.append(b)
         so = device.SO_COORDINATE if sorting_order == sam.Coordinate else device.SO_KEEP
-        self.ctx.sort_markdup(so, self._markdup)           # the Finalize node
+        opticals = any(isinstance(a, _DeviceOp) and a.kind == "markdup" and a.kw["alsoOpticals"] for a in alignment_filters)
+        self.ctx.sort_markdup(so, (2 if opticals else 1) if self._markdup else 0)           # the Finalize node
 
     # -- PipelineInput.RunPipeline (sam/filter-pipeline.go:242-279): the Sam is the source of a later phase
     def RunPipeline(self, output, hdr_filters, sorting_order):

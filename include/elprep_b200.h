@@ -34,6 +34,7 @@ extern "C" {
 #define ELP_EREFEND (-14)    /* eligible read runs past the end of its contig (Go: index out of range in computeSnpEvents) */
 #define ELP_ELIMIT (-15)     /* an implementation limit was exceeded (text says which) */
 #define ELP_ESTATE (-16)     /* entry point called in the wrong phase order */
+#define ELP_ETILE (-17)      /* a QNAME tile/x/y field that strconv.ParseInt rejects (filters/mark-optical-duplicates.go:57-64) */
 
 /* sam.SortingOrder (sam/sam-types.go:40-58) */
 #define ELP_SO_KEEP 0
@@ -108,8 +109,35 @@ uint64_t elp_n_reads(const elp_ctx *ctx);
 
 /* filters.MarkDuplicates (filters/mark-duplicates.go:406-445) + By(CoordinateLess).ParallelStableSort in the
  * Finalize of (*sam.Sam).AddNodes (sam/filter-pipeline.go:113-117, sam/sam-types.go:425-473,639-641).
- * sorting_order: ELP_SO_COORDINATE sorts; KEEP/UNKNOWN/UNSORTED leave arrival order. */
+ * sorting_order: ELP_SO_COORDINATE sorts; KEEP/UNKNOWN/UNSORTED leave arrival order.
+ * mark_duplicates: 0 none, ELP_MARKDUP = MarkDuplicates(false), ELP_MARKDUP_OPTICAL = MarkDuplicates(true) followed by
+ * filters.MarkOpticalDuplicates(reads, pairs, optical_pixel_distance) (filters/mark-optical-duplicates.go:468-517,
+ * cmd/filter.go:782) -- the metrics are read with the elp_optical_* calls below. */
+#define ELP_MARKDUP 1
+#define ELP_MARKDUP_OPTICAL 2
 int elp_sort_markdup(elp_ctx *ctx, int sorting_order, int mark_duplicates);
+
+/* ---- phase 2: duplication metrics, map[string]*DuplicatesCtr (filters/mark-optical-duplicates.go:95-110).
+ * Libraries are addressed by slot: 0 = "Unknown Library" (reads without LB), 1.. = distinct @RG LB values in header order. */
+typedef struct {
+    int64_t unpaired_reads_examined, read_pairs_examined, secondary_or_supplementary_reads, unmapped_reads,
+            unpaired_read_duplicates, read_pair_duplicates, read_pair_optical_duplicates;
+    int64_t estimated_library_size;       /* estimateLibrarySize (:533-562); 0 unless read_pairs_examined > 0 */
+    double percent_duplication;           /* NaN when nothing was examined, as in the reference (:524) */
+    double roi[100]; int32_t has_roi;     /* histogramRoi (:574-581) */
+} elp_dup_metrics;
+int32_t elp_optical_n_libraries(const elp_ctx *ctx);                    /* number of slots */
+const char *elp_optical_library_name(const elp_ctx *ctx, int32_t slot);
+int elp_optical_metrics(elp_ctx *ctx, int32_t slot, elp_dup_metrics *out);
+/* which: 0 duplicatesCountHistogram, 1 nonOpticalDuplicatesCountHistogram, 2 opticalDuplicatesCountHistogram;
+ * writes up to cap (key, count) pairs in ascending key order, returns the number of entries (-1 on error) */
+int64_t elp_optical_histogram(elp_ctx *ctx, int32_t slot, int32_t which, int64_t *keys, int64_t *counts, int64_t cap);
+/* mergeDuplicatesCtrMaps / LoadAndCombineDuplicateMetrics (:451-466, :711-731): add another worker's counters (7 values,
+ * may be NULL) and/or one of its histograms; derived metrics are recomputed on the next read-out */
+int elp_optical_merge(elp_ctx *ctx, int32_t slot, const int64_t *counters7, int32_t which, const int64_t *keys, const int64_t *counts, int64_t n);
+/* PrintDuplicatesMetrics (:601-699). The reference prints libraries in Go map order; here ascending by name.
+ * started_on replaces time.Now().Format(...) so that the output is reproducible. */
+int elp_print_duplicates_metrics(elp_ctx *ctx, const char *path, const char *command_line, const char *started_on);
 
 /* ---- phase 3: (*BaseRecalibrator).Recalibrate (filters/bqsr.go:467-551) ---- */
 int elp_bqsr_gather(elp_ctx *ctx);

@@ -145,6 +145,65 @@ def mark_duplicates(batch, header, n_threads=1, want_adapt=False):
     return (upos, score) if want_adapt else None
 
 
+class _DupMetrics(C.Structure):
+    _fields_ = [(k, C.c_int64) for k in ("unpaired_reads_examined", "read_pairs_examined", "secondary_or_supplementary", "unmapped_reads",
+                                         "unpaired_read_duplicates", "read_pair_duplicates", "read_pair_optical_duplicates",
+                                         "estimated_library_size")] + [("percent_duplication", C.c_double), ("roi", C.c_double * 100), ("has_roi", C.c_int32)]
+
+
+COUNTERS = ("unpaired_reads_examined", "read_pairs_examined", "secondary_or_supplementary", "unmapped_reads",
+            "unpaired_read_duplicates", "read_pair_duplicates", "read_pair_optical_duplicates")
+
+
+class OpticalMetrics:
+    """Result of MarkOpticalDuplicates: per slot (0 = "Unknown Library", l+1 = library l) the seven counters, the derived
+    metrics and the three count histograms as {key: count} dicts (all, non-optical, optical)."""
+
+    def __init__(self, lib_names):
+        self.lib_names = ["Unknown Library"] + list(lib_names)
+        self.counters, self.library_size, self.percent_duplication, self.roi, self.hist = [], [], [], [], []
+
+
+def markdup_optical(batch, header, order=None, pixel_distance=100, n_threads=1, metrics_path=None, command_line="", started_on=""):
+    """MarkDuplicates(alsoOpticals=True) (sets 0x400 in batch.flag in place) + MarkOpticalDuplicates over ``order``."""
+    L = lib()
+    L.orc_markdup_optical.restype = C.c_void_p
+    L.orc_optical_hist.restype = C.c_int64
+    r, h = OracleReads(batch), OracleHeader(header)
+    o = np.ascontiguousarray(order, dtype=np.int64) if order is not None else None
+    res = C.c_void_p(L.orc_markdup_optical(C.byref(r.s), C.byref(h.s), C.c_int(n_threads), _p(o), C.c_int(pixel_distance)))
+    try:
+        err = L.orc_optical_error(res)
+        if err == -1:
+            raise ValueError("Invalid QUAL character")
+        if err == -2:
+            raise ValueError("origin for duplicate read pair unknown")
+        if err == -3:
+            raise ValueError("strconv.ParseInt: parsing a QNAME tile field: invalid syntax")
+        out = OpticalMetrics(h.lib_names)
+        for slot in range(L.orc_optical_slots(res)):
+            m = _DupMetrics()
+            L.orc_optical_get(res, C.c_int(slot), C.byref(m))
+            out.counters.append({k: int(getattr(m, k)) for k in COUNTERS})
+            out.library_size.append(int(m.estimated_library_size))
+            out.percent_duplication.append(float(m.percent_duplication))
+            out.roi.append(list(m.roi) if m.has_roi else None)
+            hs = []
+            for which in range(3):
+                n = L.orc_optical_hist(res, C.c_int(slot), C.c_int(which), None, None, C.c_int64(0))
+                keys, cnt = np.zeros(n, np.int64), np.zeros(n, np.int64)
+                L.orc_optical_hist(res, C.c_int(slot), C.c_int(which), _p(keys), _p(cnt), C.c_int64(n))
+                hs.append({int(k): int(v) for k, v in zip(keys, cnt)})
+            out.hist.append(hs)
+        if metrics_path is not None:
+            arr = (C.c_char_p * max(1, len(h.lib_names)))(*[x.encode() for x in h.lib_names])
+            if L.orc_optical_print(res, arr, metrics_path.encode(), command_line.encode(), started_on.encode()) != 0:
+                raise OSError("cannot write " + metrics_path)
+        return out
+    finally:
+        L.orc_optical_free(res)
+
+
 class Reference:
     """Concatenated contig bases (1 B/base, as fasta.MappedFasta.Seq returns) + known sites."""
 

@@ -226,6 +226,16 @@ static void *smap_load_or_store(smap *m, uint64_t hash, const void *probe, int64
     pthread_mutex_unlock(&s->mu);
     *found = 0; return val;
 }
+/* Load */
+static void *smap_load(smap *m, uint64_t hash, const void *probe, int *found) {
+    hash = mix64(hash);
+    mshard *s = &m->shards[hash % (uint64_t)m->ns];
+    pthread_mutex_lock(&s->mu);
+    int64_t k = (int64_t)((hash >> 20) & (uint64_t)(s->nb - 1));
+    for (mnode *x = s->buckets[k]; x; x = x->next) if (x->hash == hash && m->eq(m->ctx, x->keyref, probe)) { void *v = x->val; pthread_mutex_unlock(&s->mu); *found = 1; return v; }
+    pthread_mutex_unlock(&s->mu);
+    *found = 0; return NULL;
+}
 /* DeleteOrStore: if present delete and return (old,1) else store and return (_,0) */
 static void *smap_delete_or_store(smap *m, uint64_t hash, const void *probe, int64_t keyref, void *val, int *deleted) {
     hash = mix64(hash);
@@ -247,7 +257,8 @@ static void *smap_delete_or_store(smap *m, uint64_t hash, const void *probe, int
 typedef struct { int32_t lb, refid, pos; int reversed; } fragment_key;               /* :188-193 */
 typedef struct { int32_t lb; int64_t aln; } pairfrag_key;                             /* :257-260 (qname via aln) */
 typedef struct { int32_t lb, refid1, refid2; int64_t pos; int rev1, rev2; } pair_key; /* :271-276 */
-typedef struct { int32_t score; int64_t aln1, aln2; pair_key key; } aln_pair;         /* :285-289 */
+typedef struct ocons { int64_t aln; struct ocons *next; } ocons;                        /* alnCons :303-306 */
+typedef struct { int32_t score; int64_t aln1, aln2; pair_key key; ocons *optical; } aln_pair; /* :285-289 */
 typedef struct { _Atomic(int64_t) object; } frag_handle;                              /* :160-174, object = aln index */
 typedef struct { _Atomic(aln_pair *) object; pair_key key; } pair_handle;
 typedef struct blk { struct blk *next; size_t used; char data[1 << 20]; } blk;
@@ -265,7 +276,7 @@ typedef struct {
     smap *fragments, *pairs_fragments, *pairs;
     frag_handle *frag_handles_unused;
     _Atomic(int64_t) next_batch; _Atomic(int) invalid;
-    arena *arenas;
+    arena *arenas; int n_arenas;
 } md_ctx;
 
 static int frag_eq(const void *ctx, int64_t kr, const void *probe) {
@@ -337,7 +348,7 @@ static void classify_pair(md_ctx *c, int64_t aln, arena *ar) { /* :329-396 */
         rev1 = (r->flag[aln1] & 0x10) != 0; rev2 = (r->flag[aln2] & 0x10) != 0;
     }
     pair_key key = {c->lib[aln1], refid1, refid2, (int64_t)((uint64_t)(int64_t)pos1 << 32) + (int64_t)pos2, rev1, rev2};
-    aln_pair *np = (aln_pair *)arena_alloc(ar, sizeof(aln_pair)); np->score = score; np->aln1 = aln1; np->aln2 = aln2; np->key = key;
+    aln_pair *np = (aln_pair *)arena_alloc(ar, sizeof(aln_pair)); np->score = score; np->aln1 = aln1; np->aln2 = aln2; np->key = key; np->optical = NULL;
     pair_handle *nh = (pair_handle *)arena_alloc(ar, sizeof(pair_handle)); atomic_init(&nh->object, np); nh->key = key;
     int found;
     uint64_t hash = (uint64_t)(uint32_t)key.lb * 0x9E3779B97F4A7C15ULL ^ (uint64_t)(uint32_t)refid1 ^ ((uint64_t)(uint32_t)refid2 << 7) ^ (uint64_t)key.pos ^ ((uint64_t)rev1 << 62) ^ ((uint64_t)rev2 << 63);
@@ -374,24 +385,275 @@ static void md_worker(void *p, int tid, int nt) {
     }
 }
 
+static void md_init(md_ctx *c, const orc_reads *r, const orc_header *h, int nt) {
+    memset(c, 0, sizeof(*c)); c->r = r; c->h = h;
+    int64_t n = r->n > 0 ? r->n : 1;
+    c->upos = (int32_t *)calloc(n, 4); c->score = (int32_t *)calloc(n, 4); c->lib = (int32_t *)malloc(n * 4);
+    for (int64_t i = 0; i < r->n; i++) c->lib[i] = -1;
+    int splits = 16 * nt; /* :407 */
+    c->fragments = smap_new(splits, frag_eq, c); c->pairs_fragments = smap_new(splits, pairfrag_eq, c); c->pairs = smap_new(splits, pair_eq, c);
+    c->arenas = (arena *)calloc(nt, sizeof(arena)); c->n_arenas = nt;
+    atomic_init(&c->next_batch, 0); atomic_init(&c->invalid, 0);
+}
+static void md_free(md_ctx *c) {
+    smap_free(c->fragments); smap_free(c->pairs_fragments); smap_free(c->pairs);
+    for (int i = 0; i < c->n_arenas; i++) arena_free(&c->arenas[i]);
+    free(c->arenas); free(c->upos); free(c->score); free(c->lib);
+}
+
 int orc_mark_duplicates(const orc_reads *r, const orc_header *h, int nt, int32_t *upos_out, int32_t *score_out) {
     if (nt < 1) nt = 1;
-    md_ctx c; memset(&c, 0, sizeof(c)); c.r = r; c.h = h;
-    int64_t n = r->n > 0 ? r->n : 1;
-    c.upos = (int32_t *)calloc(n, 4); c.score = (int32_t *)calloc(n, 4); c.lib = (int32_t *)malloc(n * 4);
-    for (int64_t i = 0; i < r->n; i++) c.lib[i] = -1;
-    int splits = 16 * nt; /* :407 */
-    c.fragments = smap_new(splits, frag_eq, &c); c.pairs_fragments = smap_new(splits, pairfrag_eq, &c); c.pairs = smap_new(splits, pair_eq, &c);
-    c.arenas = (arena *)calloc(nt, sizeof(arena));
-    atomic_init(&c.next_batch, 0); atomic_init(&c.invalid, 0);
+    md_ctx c; md_init(&c, r, h, nt);
     parallel_run(nt, md_worker, &c);
     if (upos_out) memcpy(upos_out, c.upos, r->n * 4);
     if (score_out) memcpy(score_out, c.score, r->n * 4);
     int inv = atomic_load(&c.invalid);
-    smap_free(c.fragments); smap_free(c.pairs_fragments); smap_free(c.pairs);
-    for (int i = 0; i < nt; i++) arena_free(&c.arenas[i]);
-    free(c.arenas); free(c.upos); free(c.score); free(c.lib);
+    md_free(&c);
     return inv ? -1 : 0;
+}
+
+/* ---------------------------------------------- filters/mark-optical-duplicates.go (+ graph.go, unpedantic.go:32-34) */
+typedef struct { int64_t t, x, y; } tile_info;
+/* strconv.ParseInt(s, 10, 64) as internal.ParseInt uses it (internal/strconv.go:27-33): optional sign, digits only */
+static int parse_int64(const uint8_t *s, int64_t n, int64_t *out) {
+    int64_t i = 0; int neg = 0;
+    if (n > 0 && (s[0] == '+' || s[0] == '-')) { neg = s[0] == '-'; i = 1; }
+    if (i >= n) return -1;
+    uint64_t v = 0, lim = neg ? (uint64_t)1 << 63 : ((uint64_t)1 << 63) - 1;
+    for (; i < n; i++) {
+        if (s[i] < '0' || s[i] > '9') return -1;
+        uint64_t d = (uint64_t)(s[i] - '0');
+        if (v > (lim - d) / 10) return -1; /* value out of range */
+        v = v * 10 + d;
+    }
+    *out = neg ? (int64_t)(0 - v) : (int64_t)v;
+    return 0;
+}
+/* computeTileInfo :50-71. returns -1 where the reference panics (a field that does not parse) */
+static int compute_tile_info(const orc_reads *r, int64_t aln, tile_info *ti) {
+    const uint8_t *q = r->qname + r->qname_off[aln]; int64_t n = (int64_t)(r->qname_off[aln + 1] - r->qname_off[aln]);
+    int64_t start[8], end[8]; int nc = 0; int64_t b = 0;
+    for (int64_t i = 0; i <= n; i++) if (i == n || q[i] == ':') { if (nc < 8) { start[nc] = b; end[nc] = i; } nc++; b = i + 1; }
+    int f0;
+    if (nc == 7) f0 = 4; else if (nc == 5) f0 = 2; else { ti->t = ti->x = ti->y = -1; return 0; }
+    if (parse_int64(q + start[f0], end[f0] - start[f0], &ti->t)) return -1;
+    if (parse_int64(q + start[f0 + 1], end[f0 + 1] - start[f0 + 1], &ti->x)) return -1;
+    if (parse_int64(q + start[f0 + 2], end[f0 + 2] - start[f0 + 2], &ti->y)) return -1;
+    return 0;
+}
+static inline int64_t abs64(int64_t v) { return v < 0 ? -v : v; }
+static int optical_short(const tile_info *a, const tile_info *b, int d) { return abs64(a->x - b->x) <= d && abs64(a->y - b->y) <= d; } /* unpedantic.go:32-34 */
+static int optical_full(const orc_reads *r, int64_t a1, const tile_info *t1, int64_t a2, const tile_info *t2, int d) { /* :82-93 */
+    if (r->rg[a1] != r->rg[a2]) return 0;
+    if (t1->t == -1 || t2->t == -1) return 0;
+    if (t1->t != t2->t) return 0;
+    return optical_short(t1, t2, d);
+}
+static int64_t uf_find(int64_t *g, int64_t x) { int64_t rep = x; while (rep != g[rep]) rep = g[rep]; while (x != rep) { int64_t nx = g[x]; g[x] = rep; x = nx; } return rep; } /* graph.go:49-60 */
+/* countOpticalDuplicatesFromSlice :329-373 (+ countOpticalDuplicatesWithGraph :244-273). *err set where the reference panics */
+static int64_t count_optical_from_slice(const orc_reads *r, const int64_t *dups, int64_t n, int d, int *err) {
+    if (n > 300000) return 0;
+    if (n < 2) return 0;
+    tile_info *ti = (tile_info *)malloc(sizeof(tile_info) * n);
+    for (int64_t i = 0; i < n; i++) if (compute_tile_info(r, dups[i], &ti[i])) { *err = 1; free(ti); return 0; }
+    int64_t ctr = 0;
+    if (n >= 4) {
+        /* edges inside each (RG, tile) group with tile != -1; Σ(cluster size - 1) = n - number of clusters */
+        int64_t *g = (int64_t *)malloc(sizeof(int64_t) * n);
+        for (int64_t i = 0; i < n; i++) g[i] = i;
+        for (int64_t i = 0; i < n; i++) {
+            if (ti[i].t == -1) continue;
+            for (int64_t j = i + 1; j < n; j++) {
+                if (ti[j].t != ti[i].t || r->rg[dups[i]] != r->rg[dups[j]]) continue;
+                if (optical_short(&ti[i], &ti[j], d)) { int64_t a = uf_find(g, j), b = uf_find(g, i); if (a != b) g[a] = b; }
+            }
+        }
+        int64_t clusters = 0;
+        for (int64_t i = 0; i < n; i++) if (uf_find(g, i) == i) clusters++;
+        ctr = n - clusters;
+        free(g);
+    } else {
+        if (optical_full(r, dups[0], &ti[0], dups[1], &ti[1], d)) ctr++;
+        if (n >= 3) {
+            if (optical_full(r, dups[0], &ti[0], dups[2], &ti[2], d)) ctr++;
+            if (ctr != 2 && optical_full(r, dups[1], &ti[1], dups[2], &ti[2], d)) ctr++;
+        }
+    }
+    free(ti);
+    return ctr;
+}
+
+typedef struct { int64_t *v; int64_t cap; } ohist;
+static void ohist_inc(ohist *h, int64_t idx) {
+    if (idx >= h->cap) { int64_t nc = h->cap ? h->cap : 64; while (nc <= idx) nc *= 2; h->v = (int64_t *)realloc(h->v, sizeof(int64_t) * nc); memset(h->v + h->cap, 0, sizeof(int64_t) * (nc - h->cap)); h->cap = nc; }
+    h->v[idx]++;
+}
+struct orc_optical_result { int slots; orc_dup_metrics *m; ohist *hist; /* [slots][3]: all, non-optical, optical */ int error; };
+
+/* estimateLibrarySize :533-562 */
+static int64_t estimate_library_size(int64_t n_pairs, int64_t n_unique) {
+    double n = (double)n_pairs, c = (double)n_unique;
+    if (n_pairs > 0 && n_pairs - n_unique > 0) {
+        double m = 1.0, M = 100.0;
+#define OF(x) (c / (x)-1 + gm_exp(-n / (x)))
+        double fd = OF(M * c);
+        while (fd >= 0.0) { M *= 10.0; fd = OF(M * c); }
+        for (int i = 0; i < 40; i++) {
+            double rr = (m + M) / 2.0, u = OF(rr * c);
+            if (u == 0.0) break;
+            if (u > 0.0) m = rr;
+            if (u < 0.0) M = rr;
+        }
+#undef OF
+        return (int64_t)(c * ((m + M) / 2.0));
+    }
+    return 0;
+}
+/* calculateDerivedDuplicateMetrics :519-525, estimateRoi :570-572, histogramRoi :574-581 */
+void orc_derive_dup_metrics(orc_dup_metrics *m) {
+    m->has_roi = 0; m->estimated_library_size = 0;
+    if (m->read_pairs_examined > 0) {
+        m->estimated_library_size = estimate_library_size(m->read_pairs_examined - m->read_pair_optical_duplicates, m->read_pairs_examined - m->read_pair_duplicates);
+        int64_t uniq = m->read_pairs_examined - m->read_pair_duplicates;
+        for (int64_t x = 1; x <= 100; x++)
+            m->roi[x - 1] = (double)m->estimated_library_size * (1.0 - gm_exp(-(double)(x * m->read_pairs_examined) / (double)m->estimated_library_size)) / (double)uniq;
+        m->has_roi = 1;
+    }
+    m->percent_duplication = (double)(m->unpaired_read_duplicates + m->read_pair_duplicates * 2) / (double)(m->unpaired_reads_examined + m->read_pairs_examined * 2);
+}
+
+/* MarkDuplicates(alsoOpticals=true) followed by MarkOpticalDuplicates (:468-517) over the reads taken in `order`
+ * (the sorted order in the reference; NULL = as given). Sequential. */
+orc_optical_result *orc_markdup_optical(const orc_reads *r, const orc_header *h, int nt, const int64_t *order, int pixel_distance) {
+    if (nt < 1) nt = 1;
+    md_ctx c; md_init(&c, r, h, nt);
+    parallel_run(nt, md_worker, &c);
+    orc_optical_result *res = (orc_optical_result *)calloc(1, sizeof(*res));
+    int n_lib = 0; for (int i = 0; i < h->n_rg; i++) if (h->rg_lib[i] + 1 > n_lib) n_lib = h->rg_lib[i] + 1;
+    res->slots = n_lib + 1; res->m = (orc_dup_metrics *)calloc(res->slots, sizeof(orc_dup_metrics)); res->hist = (ohist *)calloc((size_t)res->slots * 3, sizeof(ohist));
+    if (atomic_load(&c.invalid)) { res->error = -1; md_free(&c); return res; }
+    /* addLIBID for all reads (:426) */
+    for (int64_t i = 0; i < r->n; i++) c.lib[i] = (r->rg[i] >= 0 && r->rg[i] < h->n_rg) ? h->rg_lib[r->rg[i]] : -1;
+    arena *ar = &c.arenas[0];
+    smap *pf = smap_new(16, pairfrag_eq, &c);
+    for (int64_t k = 0; k < r->n && !res->error; k++) {
+        int64_t aln = order ? order[k] : k;
+        orc_dup_metrics *ctr = &res->m[c.lib[aln] + 1];
+        uint16_t f = r->flag[aln];
+        if (f & 0x4) { ctr->unmapped_reads++; continue; }
+        if (f & (0x100 | 0x800)) { ctr->secondary_or_supplementary++; continue; }
+        if (is_true_fragment(f)) ctr->unpaired_reads_examined++;
+        if (is_true_pair(f)) ctr->read_pairs_examined++;
+        if (!(f & 0x400)) continue;
+        if (is_true_fragment(f)) ctr->unpaired_read_duplicates++;          /* markOpticalDuplicatesFragment :176-180 */
+        if (!is_true_pair(f)) continue;                                     /* markOpticalDuplicatesPair :182-224 */
+        pairfrag_key pk = {c.lib[aln], aln}; int deleted;
+        void *entry = smap_delete_or_store(pf, (uint64_t)(uint32_t)c.lib[aln] * 31 ^ qname_hash(r, aln), &pk, aln, (void *)(intptr_t)(aln + 1), &deleted);
+        if (!deleted) continue;
+        int64_t aln1 = aln, aln2 = (int64_t)(intptr_t)entry - 1;
+        ctr->read_pair_duplicates++;
+        int32_t refid1 = r->refid[aln1], refid2 = r->refid[aln2], pos1 = c.upos[aln1], pos2 = c.upos[aln2];
+        int rev1 = (r->flag[aln1] & 0x10) != 0, rev2 = (r->flag[aln2] & 0x10) != 0;
+        if (refid1 > refid2 || (refid1 == refid2 && (pos1 > pos2 || (pos1 == pos2 && rev1 && !rev2)))) {
+            int64_t t = aln1; aln1 = aln2; aln2 = t; int32_t t32 = refid1; refid1 = refid2; refid2 = t32; t32 = pos1; pos1 = pos2; pos2 = t32;
+            rev1 = (r->flag[aln1] & 0x10) != 0; rev2 = (r->flag[aln2] & 0x10) != 0;
+        }
+        pair_key key = {c.lib[aln1], refid1, refid2, (int64_t)((uint64_t)(int64_t)pos1 << 32) + (int64_t)pos2, rev1, rev2};
+        uint64_t hash = (uint64_t)(uint32_t)key.lb * 0x9E3779B97F4A7C15ULL ^ (uint64_t)(uint32_t)refid1 ^ ((uint64_t)(uint32_t)refid2 << 7) ^ (uint64_t)key.pos ^ ((uint64_t)rev1 << 62) ^ ((uint64_t)rev2 << 63);
+        int found;
+        pair_handle *best = (pair_handle *)smap_load(c.pairs, hash, &key, &found);
+        if (!found || !best) { res->error = -2; break; }                    /* "origin for duplicate read pair unknown" :210 */
+        aln_pair *bp = atomic_load(&best->object);
+        if (bp->aln1 != aln1) {
+            ocons *e = (ocons *)arena_alloc(ar, sizeof(ocons));
+            e->aln = (r->flag[aln1] & 0x40) ? aln1 : aln2;                  /* :216-221 */
+            e->next = bp->optical; bp->optical = e;
+        }
+    }
+    for (int i = 0; i < res->slots; i++) res->m[i].read_pairs_examined /= 2;  /* :503-505 */
+    /* countOpticalDuplicatesPairs :380-431 over every entry of the pairs map */
+    int64_t *fwd = NULL, *rev = NULL; int64_t capf = 0, capr = 0;
+    for (int si = 0; si < c.pairs->ns && !res->error; si++) {
+        mshard *s = &c.pairs->shards[si];
+        for (int64_t b = 0; b < s->nb && !res->error; b++) for (mnode *x = s->buckets[b]; x; x = x->next) {
+            aln_pair *origin = atomic_load(&((pair_handle *)x->val)->object);
+            int64_t nf = 0, nr = 0;
+            int64_t oaln = (r->flag[origin->aln1] & 0x40) ? origin->aln1 : origin->aln2;   /* countOpticalDuplicates :275-327 */
+#define PUSH(arr, nn, cap, v) do { if (nn >= cap) { cap = cap ? cap * 2 : 64; arr = (int64_t *)realloc(arr, sizeof(int64_t) * cap); } arr[nn++] = (v); } while (0)
+            if (r->flag[oaln] & 0x10) PUSH(rev, nr, capr, oaln); else PUSH(fwd, nf, capf, oaln);
+            for (ocons *e = origin->optical; e; e = e->next) {
+                if (r->flag[e->aln] & 0x10) { if (nr <= 300000) PUSH(rev, nr, capr, e->aln); }
+                else { if (nf <= 300000) PUSH(fwd, nf, capf, e->aln); }
+            }
+#undef PUSH
+            int err = 0;
+            int64_t fc = count_optical_from_slice(r, fwd, nf, pixel_distance, &err), rc = count_optical_from_slice(r, rev, nr, pixel_distance, &err);
+            if (err) { res->error = -3; break; }
+            int64_t optical = fc + rc, dupcount = nf + nr;
+            int slot = c.lib[origin->aln1] + 1;
+            res->m[slot].read_pair_optical_duplicates += optical;
+            ohist *hh = &res->hist[(size_t)slot * 3];
+            ohist_inc(&hh[0], dupcount);                                    /* incrementDuplicatesCountsHistograms :150-174 */
+            if (dupcount - optical > 0) ohist_inc(&hh[1], dupcount - optical);
+            if (optical > 0) ohist_inc(&hh[2], optical + 1);
+        }
+    }
+    free(fwd); free(rev);
+    for (int i = 0; i < res->slots; i++) orc_derive_dup_metrics(&res->m[i]);
+    smap_free(pf);
+    md_free(&c);
+    return res;
+}
+int orc_optical_error(const orc_optical_result *res) { return res->error; }
+int orc_optical_slots(const orc_optical_result *res) { return res->slots; }
+void orc_optical_get(const orc_optical_result *res, int slot, orc_dup_metrics *out) { *out = res->m[slot]; }
+int64_t orc_optical_hist(const orc_optical_result *res, int slot, int which, int64_t *keys, int64_t *counts, int64_t cap) {
+    const ohist *h = &res->hist[(size_t)slot * 3 + which]; int64_t n = 0;
+    for (int64_t i = 0; i < h->cap; i++) if (h->v[i]) { if (n < cap) { keys[n] = i; counts[n] = h->v[i]; } n++; }
+    return n;
+}
+void orc_optical_free(orc_optical_result *res) {
+    if (!res) return;
+    for (int i = 0; i < res->slots * 3; i++) free(res->hist[i].v);
+    free(res->hist); free(res->m); free(res);
+}
+/* formatFloat :583-599 */
+static void format_float(double f, char *out) {
+    if (f != f) { strcpy(out, "NaN"); return; }
+    sprintf(out, "%.6f", f);
+    char *dot = strchr(out, '.'); if (!dot) return;
+    for (char *j = out + strlen(out) - 1; j > dot; j--) if (*j != '0') { j[1] = 0; return; }
+}
+/* PrintDuplicatesMetrics :601-699. Go iterates its map in random order; here: libraries in ascending name order
+ * ("Unknown Library" = slot 0 takes its place by name). lib_names[slots-1]. */
+int orc_optical_print(const orc_optical_result *res, const char *const *lib_names, const char *path, const char *command_line, const char *started_on) {
+    FILE *f = fopen(path, "w"); if (!f) return -1;
+    int n = res->slots; int *ord = (int *)malloc(sizeof(int) * n); const char **nm = (const char **)malloc(sizeof(char *) * n);
+    for (int i = 0; i < n; i++) { ord[i] = i; nm[i] = i == 0 ? "Unknown Library" : lib_names[i - 1]; }
+    for (int i = 1; i < n; i++) for (int j = i; j > 0 && strcmp(nm[ord[j]], nm[ord[j - 1]]) < 0; j--) { int t = ord[j]; ord[j] = ord[j - 1]; ord[j - 1] = t; }
+    fprintf(f, "## htsjdk.samtools.metrics.StringHeader\n# %s\n## htsjdk.samtools.metrics.StringHeader\n# Started on: %s\n\n## METRICS CLASS\tpicard.sam.DuplicationMetrics\n", command_line, started_on);
+    fprintf(f, "LIBRARY\tUNPAIRED_READS_EXAMINED\tREAD_PAIRS_EXAMINED\tSECONDARY_OR_SUPPLEMENTARY_RDS\tUNMAPPED_READS\tUNPAIRED_READ_DUPLICATES\tREAD_PAIR_DUPLICATES\tREAD_PAIR_OPTICAL_DUPLICATES\tPERCENT_DUPLICATION\tESTIMATED_LIBRARY_SIZE\n");
+    char buf[64]; int the = -1, many = 0;
+    for (int k = 0; k < n; k++) {
+        const orc_dup_metrics *m = &res->m[ord[k]];
+        format_float(m->percent_duplication, buf);
+        fprintf(f, "%s\t%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t%lld\t%s", nm[ord[k]], (long long)m->unpaired_reads_examined, (long long)m->read_pairs_examined, (long long)m->secondary_or_supplementary,
+                (long long)m->unmapped_reads, (long long)m->unpaired_read_duplicates, (long long)m->read_pair_duplicates, (long long)m->read_pair_optical_duplicates, buf);
+        if (m->read_pairs_examined > 0) { fprintf(f, "\t%lld", (long long)m->estimated_library_size); if (the >= 0) many = 1; the = ord[k]; }
+        fprintf(f, "\n");
+    }
+    fprintf(f, "\n");
+    if (many || the < 0) { fprintf(f, "\n"); fclose(f); free(ord); free(nm); return 0; }
+    const orc_dup_metrics *m = &res->m[the]; const ohist *hh = &res->hist[(size_t)the * 3];
+#define HV(w, k) ((k) < hh[w].cap ? (long long)hh[w].v[k] : 0LL)
+    fprintf(f, "## HISTOGRAM\tjava.lang.Double\nBIN\tCoverageMult\tall_sets\toptical_sets\tnon_optical_sets\n");
+    for (int i = 0; i < 100; i++) { format_float(m->roi[i], buf); fprintf(f, "%d.0\t%s\t%lld\t%lld\t%lld\n", i + 1, buf, HV(0, i + 1), HV(2, i + 1), HV(1, i + 1)); }
+    int64_t maxk = 0; for (int w = 0; w < 3; w++) if (hh[w].cap > maxk) maxk = hh[w].cap;
+    for (int64_t k = 101; k < maxk; k++) if (HV(0, k) || HV(1, k) || HV(2, k)) fprintf(f, "%lld.0\t0\t%lld\t%lld\t%lld\n", (long long)k, HV(0, k), HV(2, k), HV(1, k));
+#undef HV
+    fprintf(f, "\n");
+    fclose(f); free(ord); free(nm);
+    return 0;
 }
 
 /* ---------------------------------------------- intervals/intervals.go:88-173 */

@@ -71,6 +71,27 @@ int orc_coordinate_sort(const orc_reads *r, int64_t *perm, int n_threads);
  * upos_out/score_out optional (may be NULL). returns 0, or -1 on "Invalid QUAL character". */
 int orc_mark_duplicates(const orc_reads *r, const orc_header *h, int n_threads, int32_t *upos_out, int32_t *score_out);
 
+/* filters/mark-optical-duplicates.go:95-110 (DuplicatesCtr) + the derived metrics (:519-581) */
+typedef struct {
+    int64_t unpaired_reads_examined, read_pairs_examined, secondary_or_supplementary, unmapped_reads,
+            unpaired_read_duplicates, read_pair_duplicates, read_pair_optical_duplicates;
+    int64_t estimated_library_size; double percent_duplication; double roi[100]; int32_t has_roi;
+} orc_dup_metrics;
+typedef struct orc_optical_result orc_optical_result;
+/* MarkDuplicates(alsoOpticals = true) + MarkOpticalDuplicates (mark-optical-duplicates.go:468-517) with the reads visited
+ * in `order` (NULL = as given). Slot 0 = "Unknown Library", slot l+1 = library id l. error(): 0, -1 invalid QUAL,
+ * -2 "origin for duplicate read pair unknown", -3 a QNAME tile/x/y field that strconv.ParseInt rejects. */
+orc_optical_result *orc_markdup_optical(const orc_reads *r, const orc_header *h, int n_threads, const int64_t *order, int pixel_distance);
+int orc_optical_error(const orc_optical_result *res);
+int orc_optical_slots(const orc_optical_result *res);
+void orc_optical_get(const orc_optical_result *res, int slot, orc_dup_metrics *out);
+/* which: 0 duplicatesCountHistogram, 1 nonOptical..., 2 optical...; returns number of non-zero entries (ascending key) */
+int64_t orc_optical_hist(const orc_optical_result *res, int slot, int which, int64_t *keys, int64_t *counts, int64_t cap);
+void orc_optical_free(orc_optical_result *res);
+void orc_derive_dup_metrics(orc_dup_metrics *m);
+/* PrintDuplicatesMetrics (:601-699); libraries printed in ascending name order (the reference iterates a Go map) */
+int orc_optical_print(const orc_optical_result *res, const char *const *lib_names, const char *path, const char *command_line, const char *started_on);
+
 /* intervals/intervals.go:103-173 (KATs from intervals/intervals_test.go) */
 int64_t orc_flatten(int32_t *se, int64_t n);            /* in place, returns new count */
 int orc_overlap(const int32_t *se, int64_t n, int32_t start, int32_t end);

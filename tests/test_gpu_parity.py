@@ -204,3 +204,101 @@ def test_reference_style_api():
     o = oracle_pipeline(w)
     assert np.array_equal(out.record_index, o["perm"]) and np.array_equal(out.flag, o["flag"])
     assert np.array_equal(out.qual[:int(out.qual_off[-1])], o["qual"]) and report == o["report"]
+
+
+# ---- duplication metrics / optical duplicates (filters.MarkOpticalDuplicates) ----
+def _optical_both(w, pixel=100, n_batches=1, tmp=None):
+    import oracle
+    from elprep_b200 import device, _lib
+    b = w.batch.copy()
+    oracle.mark_duplicates(b, w.header, n_threads=1)
+    perm = oracle.coordinate_sort(b, n_threads=4)                       # the reference visits the sorted reads (:470-494)
+    b2 = w.batch.copy()
+    om = oracle.markdup_optical(b2, w.header, order=perm, pixel_distance=pixel,
+                                metrics_path=(tmp + "/o.txt") if tmp else None, command_line="elprep filter a b", started_on="now")
+    ctx = device.Context(w.header, optical_pixel_distance=pixel)
+    n = w.batch.n
+    bounds = [n * i // n_batches for i in range(n_batches + 1)]
+    for a, e in zip(bounds[:-1], bounds[1:]):
+        ctx.append(w.batch.take(np.arange(a, e)))
+    ctx.sort_markdup(device.SO_COORDINATE, _lib.MARKDUP_OPTICAL)
+    gm = ctx.optical_metrics()
+    assert ctx.optical_libraries() == om.lib_names
+    idx, flag, _, _ = ctx.fetch()
+    assert np.array_equal(idx, perm.astype(np.uint64)) and np.array_equal(flag, b2.flag[perm])
+    for slot, g in enumerate(gm):
+        for k_g, k_o in zip(_lib.ElpDupMetrics.COUNTERS, oracle.COUNTERS):
+            assert g[k_g] == om.counters[slot][k_o], (slot, k_g)
+        assert g["hist"] == om.hist[slot], slot
+        assert g["estimated_library_size"] == om.library_size[slot]
+        assert g["percent_duplication"] == om.percent_duplication[slot] or (np.isnan(g["percent_duplication"]) and np.isnan(om.percent_duplication[slot]))
+        assert g["roi"] == om.roi[slot]
+    if tmp:
+        ctx.print_duplicates_metrics(tmp + "/g.txt", "elprep filter a b", "now")
+        assert open(tmp + "/g.txt").read() == open(tmp + "/o.txt").read()
+    ctx.close()
+    return om
+
+
+@pytest.mark.parametrize("seed,kw", [(3, dict(dup_frac=0.3, optical_frac=0.4)), (4, dict(dup_frac=0.1, optical_frac=0.2, n_rg=1)),
+                                     (5, dict(dup_frac=0.5, optical_frac=0.5, unmapped_frac=0.2, exome=True))])
+def test_optical_metrics(seed, kw, tmp_path):
+    w = synth.make_workload(20_000, SMALL, seed=seed, want_reference=False, **kw)
+    om = _optical_both(w, n_batches=3, tmp=str(tmp_path))
+    assert sum(c["read_pair_optical_duplicates"] for c in om.counters) > 100
+
+
+def test_optical_long_runs_and_pixel_distance(tmp_path):
+    # 97 % duplicates of ~100 roots: runs far longer than 32 pairs take the block kernel (lock-free union-find)
+    w = synth.make_workload(4_000, [("chr20", 200_000)], seed=9, dup_frac=0.97, optical_frac=0.6, unmapped_frac=0.0, want_reference=False, n_rg=1)
+    om = _optical_both(w, tmp=str(tmp_path))
+    assert max(max(h[0]) for h in om.hist if h[0]) > 64
+    _optical_both(w, pixel=10)
+    _optical_both(w, pixel=3000)
+
+
+def test_optical_hand_cases():
+    from elprep_b200 import device, _lib
+    import oracle
+    h = sam.Header(sq=[{"SN": "chr1", "LN": 100000}], rg=[{"ID": "rg1", "LB": "libA"}, {"ID": "rg2", "LB": "libA"}, {"ID": "rg3"}])
+    def R(q, flag, pos, score, rg="rg1", **kw):
+        return dict(QNAME=q, FLAG=flag, RNAME="chr1", POS=pos, CIGAR="4M", SEQ="ACGT", QUAL=[score] * 4, RG=rg, **kw)
+    def pair(q, p1, p2, score, flags=(99, 147), rg="rg1"):
+        return [R(q, flags[0], p1, score, RNEXT="=", PNEXT=p2, rg=rg), R(q, flags[1], p2, score, RNEXT="=", PNEXT=p1, rg=rg)]
+    cases = {
+        "strand lists": pair("M:1:F:1:7:100:100", 100, 300, 40) + pair("M:2:F:1:7:101:101", 100, 300, 30) + pair("M:3:F:1:7:102:102", 100, 300, 20, flags=(163, 83)),
+        "read groups": pair("M:1:F:1:7:100:100", 100, 300, 40) + pair("M:2:F:1:7:101:101", 100, 300, 30, rg="rg2"),
+        "five columns": pair("F:1:7:100:200", 100, 300, 40) + pair("F:1:7:110:210", 100, 300, 30),
+        "no tile info": pair("a:7:100:200", 100, 300, 40) + pair("b:7:100:200", 100, 300, 30),
+        "signs": pair("F:1:+7:-5:+20", 100, 300, 40) + pair("F:1:7:5:20", 100, 300, 30),
+        "unparsed singleton": pair("F:1:7:100:2x0", 100, 300, 40) + pair("F:1:7:110:210", 500, 700, 30),
+        "preset flags": pair("M:1:F:1:1:10:10", 100, 300, 40, flags=(99 | 0x400, 147 | 0x400)) + pair("M:2:F:1:1:20:20", 100, 300, 30),
+        "single pair": pair("M:1:F:1:1:10:10", 100, 300, 40),
+        "no pairs": [R("f1", 0, 10, 30), R("f2", 0, 10, 20), R("u", 4, 0, 30), R("n", 0, 50, 30, rg="rg3")],
+    }
+    for name, recs in cases.items():
+        b = sam.AlignmentBatch.from_records(h, recs)
+        om = oracle.markdup_optical(b.copy(), h)
+        ctx = device.Context(h)
+        ctx.append(b)
+        ctx.sort_markdup(device.SO_KEEP, _lib.MARKDUP_OPTICAL)
+        gm = ctx.optical_metrics()
+        for slot, g in enumerate(gm):
+            assert [g[k] for k in _lib.ElpDupMetrics.COUNTERS] == [om.counters[slot][k] for k in oracle.COUNTERS], name
+            assert g["hist"] == om.hist[slot], name
+        ctx.close()
+    # a tile field that does not parse, inside a list of two: the reference panics in strconv.ParseInt
+    b = sam.AlignmentBatch.from_records(h, pair("F:1:7:100:2x0", 100, 300, 40) + pair("F:1:7:110:210", 100, 300, 30))
+    ctx = device.Context(h)
+    ctx.append(b)
+    with pytest.raises(device.ElprepError) as ei:
+        ctx.sort_markdup(device.SO_KEEP, _lib.MARKDUP_OPTICAL)
+    assert ei.value.code == -17 and "ParseInt" in str(ei.value)
+    ctx.close()
+    # metrics asked for without the optical pass
+    ctx = device.Context(h)
+    ctx.append(b)
+    ctx.sort_markdup(device.SO_KEEP, True)
+    with pytest.raises(device.ElprepError):
+        ctx.optical_metrics()
+    ctx.close()
