@@ -45,10 +45,11 @@ template <class T> int grow(elp_ctx* c, DBuf<T>& b, size_t need, size_t keep) {
 int upload_side_inputs(elp_ctx* c) {
     if (!c->side_dirty) return E_OK;
     const int nc = c->n_contigs;
-    std::vector<const uint8_t*> rp(nc); std::vector<const int32_t*> sp(nc);
-    for (int i = 0; i < nc; i++) { rp[i] = c->d_ref[i]; sp[i] = c->d_sites[i]; }
+    std::vector<const uint8_t*> rp(nc), np(nc); std::vector<const int32_t*> sp(nc);
+    for (int i = 0; i < nc; i++) { rp[i] = c->d_ref[i]; np[i] = c->d_refnib_raw[i] ? c->d_refnib_raw[i] + 32 : nullptr; sp[i] = c->d_sites[i]; }
     if (nc) {
         CUDA_TRY(c, cudaMemcpyAsync(c->d_ref_ptrs, rp.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_refnib_ptrs, np.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_ref_len, c->ref_len.data(), nc * 8, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_site_ptrs, sp.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_n_sites, c->n_sites.data(), nc * 8, cudaMemcpyHostToDevice, c->stream));
@@ -102,7 +103,7 @@ int elp_create(const elp_config* cfg, elp_ctx** out) {
     const int nc = std::max(1, c->n_contigs), nr = std::max(1, c->n_rg);
     bool ok = cudaMalloc(&c->d_rg_lib, nr * 4) == cudaSuccess && cudaMalloc(&c->d_rg_cov, nr * 4) == cudaSuccess && cudaMalloc(&c->d_contig_len, nc * 4) == cudaSuccess &&
               cudaMalloc(&c->d_ranges, sizeof(DeviceRanges)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess &&
-              cudaMalloc(&c->d_ref_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_ref_len, nc * 8) == cudaSuccess &&
+              cudaMalloc(&c->d_ref_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_refnib_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_ref_len, nc * 8) == cudaSuccess &&
               cudaMalloc(&c->d_site_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_n_sites, nc * 8) == cudaSuccess &&
               cudaMalloc(&c->d_tables, std::max<size_t>(16, c->geom.cells() * 2 * sizeof(int64_t))) == cudaSuccess;
     if (!ok) { c->err = "device allocation failed in elp_create"; return bail(ELP_ENOMEM); }
@@ -110,7 +111,7 @@ int elp_create(const elp_config* cfg, elp_ctx** out) {
     if (c->n_contigs) cudaMemcpy(c->d_contig_len, c->contig_len.data(), c->n_contigs * 4, cudaMemcpyHostToDevice);
     cudaMemset(c->d_err, 0, 4);
     cudaMemset(c->d_tables, 0, std::max<size_t>(16, c->geom.cells() * 2 * sizeof(int64_t)));
-    c->d_ref.assign(c->n_contigs, nullptr); c->ref_len.assign(c->n_contigs, 0);
+    c->d_ref.assign(c->n_contigs, nullptr); c->d_refnib_raw.assign(c->n_contigs, nullptr); c->ref_len.assign(c->n_contigs, 0);
     c->d_sites.assign(c->n_contigs, nullptr); c->n_sites.assign(c->n_contigs, 0);
     if ((e = cudaGetLastError()) != cudaSuccess) { c->err = std::string("elp_create: ") + cudaGetErrorString(e); return bail(ELP_ECUDA); }
     *out = c;
@@ -122,8 +123,9 @@ void elp_destroy(elp_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto p : c->d_ref) if (p) cudaFree(p);
+    for (auto p : c->d_refnib_raw) if (p) cudaFree(p);
     for (auto p : c->d_sites) if (p) cudaFree(p);
-    void* singles[] = {c->d_rg_lib, c->d_rg_cov, c->d_contig_len, c->d_ranges, c->d_err, (void*)c->d_ref_ptrs, c->d_ref_len, (void*)c->d_site_ptrs, c->d_n_sites, c->d_tables,
+    void* singles[] = {c->d_rg_lib, c->d_rg_cov, c->d_contig_len, c->d_ranges, c->d_err, (void*)c->d_ref_ptrs, (void*)c->d_refnib_ptrs, c->d_ref_len, (void*)c->d_site_ptrs, c->d_n_sites, c->d_tables,
                        c->d_lut, c->d_cov_exists, c->d_opt_ctr, c->d_opt_hist, c->d_opt_ovf, c->d_opt_small, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
     for (void* p : singles) if (p) cudaFree(p);
     c->refid.release(); c->pos.release(); c->nref.release(); c->pnext.release(); c->tlen.release(); c->rg.release(); c->flag.release(); c->mapq.release();
@@ -171,7 +173,7 @@ int elp_set_reference(elp_ctx* c, int32_t contig, const uint8_t* bases, uint64_t
     CUDA_TRY(c, cudaMalloc(&c->d_ref[contig], n + 16));
     CUDA_TRY(c, cudaMemcpy(c->d_ref[contig], bases, n, cudaMemcpyHostToDevice));
     c->ref_len[contig] = n; c->side_dirty = true;
-    return ELP_OK;
+    return pack_reference(c, contig);
 }
 
 int elp_set_known_sites(elp_ctx* c, int32_t contig, const int32_t* se, uint64_t n_intervals, int already_flat) {

@@ -168,14 +168,17 @@ __device__ void hard_clip(Clip& a, int start, int stop) {
 
 // ---------------------------------------------------------------- per-read descriptor written by the prep kernel
 struct __align__(16) ReadDesc {
+    uint64_t qloc;            // QUAL arena offset of the first kept base | refid << 40
+    uint64_t nloc;            // SEQ nibble index of the first kept base (2 * seq_off + c_s0)
     int32_t c_pos;            // POS after clipping (1-based)
     uint16_t c_s0, c_len;     // kept bases [c_s0, c_s0 + c_len) of the original read; c_len == 0: not recalibrated
     uint8_t flags, cov, n_skip, pad;
     uint32_t ovf;             // slot of the 512-bit skip bitmask when more than 4 known-site ranges hit the read
     uint16_t skip[4][2];      // inclusive [first,last] clipped read coordinates masked by known sites
-};
-constexpr uint8_t DF_REVERSED = 1, DF_LAST = 2, DF_SINGLE_M = 4, DF_SKIP_OVF = 8;
+};                            // 48 bytes = three 16-byte loads: location | scalars | skip ranges
+constexpr uint8_t DF_REVERSED = 1, DF_LAST = 2, DF_SINGLE_M = 4, DF_SKIP_OVF = 8, DF_LEAN = 16;
 constexpr int OVF_WORDS = 16;   // 512 bits
+constexpr int CHUNK = 16;       // bases per lane in the chunk kernel
 
 struct GatherArgs {
     uint64_t n;
@@ -188,19 +191,26 @@ struct GatherArgs {
     const int32_t* const* sites; const uint64_t* n_sites;
     TableGeom geom; unsigned long long* tables; uint32_t* err;
     ReadDesc* desc; uint32_t* ovf_bits; uint32_t* ovf_count; uint32_t ovf_cap;
+    const uint8_t* const* refnib;    // per contig: reference base codes, 4 bits per base, low nibble first
+    uint32_t* gen_list; uint32_t* gen_count;   // reads that take the general (warp per read) kernel
+    int lanes_per_read;              // chunk kernel: lanes (16-base chunks) reserved per read
     // shared-memory privatisation: observation counters of the frequent QUAL values live in shared memory
-    int8_t qslot[94]; uint8_t slot_q[94]; int n_slots, Lc, ncols_s;
+    int8_t qslot[94]; uint8_t slot_q[94]; int n_slots, Lc;
+    int ncols_s, ctx_col_s;          // chunk kernel rows: skewed cycle cells [0, ctx_col_s), then 16 context cells
 };
 
 // ---------------------------------------------------------------- kernel A: one thread per read
 __global__ void __launch_bounds__(128) bqsr_prep_kernel(GatherArgs A) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= A.n) return;
-    ReadDesc d; d.c_pos = 0; d.c_s0 = 0; d.c_len = 0; d.flags = 0; d.cov = 0; d.n_skip = 0; d.pad = 0; d.ovf = 0;
+    ReadDesc d; d.qloc = 0; d.nloc = 0; d.c_pos = 0; d.c_s0 = 0; d.c_len = 0; d.flags = 0; d.cov = 0; d.n_skip = 0; d.pad = 0; d.ovf = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++) { d.skip[r][0] = 0; d.skip[r][1] = 0; }
     ReadDesc* out = A.desc + k;
-    auto done = [&]() { *reinterpret_cast<uint4*>(out) = *reinterpret_cast<const uint4*>(&d); *(reinterpret_cast<uint4*>(out) + 1) = *(reinterpret_cast<const uint4*>(&d) + 1); };
+    auto done = [&]() {
+        const uint4* src = reinterpret_cast<const uint4*>(&d); uint4* dst = reinterpret_cast<uint4*>(out);
+        dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2];
+    };
     // ---- recalibrateAln, bqsr.go:225-244 ----
     const uint16_t f = A.flag[k];
     const uint8_t mq = A.mapq[k];
@@ -258,6 +268,8 @@ __global__ void __launch_bounds__(128) bqsr_prep_kernel(GatherArgs A) {
     int n_m = 0, n_other = 0;
     for (int i = 0; i < a.nc; i++) { const int o = op_of(a.cg[i]); if (o == 0 || o == 7 || o == 8) n_m++; else if (o != 5) n_other++; }
     d.c_pos = a.pos; d.c_s0 = (uint16_t)a.s0; d.c_len = (uint16_t)L; d.cov = (uint8_t)A.rg_cov[g];
+    d.qloc = (A.qual_off[k] + (uint64_t)a.s0) | ((uint64_t)(uint32_t)refid << 40);
+    d.nloc = A.seq_off[k] * 2 + (uint64_t)a.s0;
     d.flags = ((f & F_REVERSED) ? DF_REVERSED : 0) | ((f & F_LAST) ? DF_LAST : 0) | ((n_m == 1 && n_other == 0) ? DF_SINGLE_M : 0);
     // ---- known sites (calculateSkipSlice, bqsr.go:389-414): the clipped read has no S, so softStart/softEnd = POS / End ----
     const uint64_t ns = A.n_sites[refid];
@@ -296,14 +308,17 @@ __global__ void __launch_bounds__(128) bqsr_prep_kernel(GatherArgs A) {
             d.flags |= DF_SKIP_OVF; d.ovf = slot;
         }
     }
+    // chunk kernel: one M run, every cycle inside --max-cycle (|cycle| <= L), inside the contig, fits the lanes of a read
+    if ((d.flags & DF_SINGLE_M) && !(d.flags & DF_SKIP_OVF) && L <= A.geom.max_cycle && L <= CHUNK * A.lanes_per_read &&
+        (uint64_t)(a.pos - 1) + (uint64_t)L <= A.ref_len[refid]) d.flags |= DF_LEAN;
     done();
 }
 
-// ---------------------------------------------------------------- kernel B: one warp per read, one lane per base
+// ---------------------------------------------------------------- shared helpers of the two counting kernels
 // base code of a BAM nibble: A C G T -> 0..3, everything else 8 (bit 3 = "not ACGT", bqsr.go:509)
 __device__ __forceinline__ uint32_t nib_code(uint32_t nib) { return (uint32_t)((0x8888888388828108ull >> (4 * nib)) & 0xfull); }
 
-// rare per-base events of the lean path, out of line: QUAL without a shared-memory slot, QUAL > 93, base past the contig end
+// rare per-base events, out of line: QUAL without a shared-memory slot, QUAL > 93, base past the contig end
 __device__ __noinline__ void count_rare(const GatherArgs& A, int cov, int q, int cyc, uint32_t ctx, bool okc, uint32_t snp, bool past_end, uint32_t* errbits) {
     if (q > 93) { *errbits |= DERR_QUAL_RANGE; return; }
     if (past_end) { *errbits |= DERR_REFEND; return; }
@@ -316,98 +331,241 @@ __device__ __noinline__ void count_rare(const GatherArgs& A, int cov, int q, int
 }
 
 // shared memory through explicit 32-bit shared-window addresses (generic pointers cost an address conversion per access)
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int lds_s8(uint32_t a) { int v; asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void reds_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
-struct LeanSmem { uint32_t obs, mis, refcode, qslot, nib; };   // shared-window byte addresses
 
-// Lean path: clipped CIGAR is a single M operation and every cycle is within --max-cycle (checked by the caller).
-// Everything loop-invariant is hoisted: per-lane byte pointers advance by constants, the neighbour base codes are software
-// pipelined (previous / current / next 32-base step) so the walk is always ascending, REV folds the strand selects away.
-template <bool REV>
-__device__ __forceinline__ void count_read_lean(const GatherArgs& A, const LeanSmem S, const uint32_t row_bytes, const uint32_t ctx_off_bytes, const int Lc,
-                                                const uint4 d0, const uint4 d1, const uint8_t* __restrict__ qualp, const uint8_t* __restrict__ seqp,
-                                                const uint8_t* __restrict__ ref, const int64_t reflen, const unsigned lane, uint32_t* errbits) {
-    const int L = (int)(d0.y >> 16), c_s0 = (int)(d0.y & 0xffff);
-    const uint32_t flags = d0.z & 0xff, cov = (d0.z >> 8) & 0xff, n_skip = (d0.z >> 16) & 0xff;
-    const int last = (flags & DF_LAST) ? 1 : 0;
-    const int64_t j0 = (int64_t)(int32_t)d0.x - 1;
-    const int nref = (int)max((int64_t)0, min((int64_t)L, reflen - j0));
-    const int nit = (L + 31) >> 5;
-    const int rof = 1 - 2 * last, inc = REV ? -rof : rof, cf = rof + (REV ? (L - 1) * rof : 0);   // prepareCycleCovariates, bqsr.go:376-383
-    // low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2
-    const uint8_t* qp = qualp + lane;
-    int leftPos = L, rightPos = -1;
-    {
-        const uint8_t* q2 = qp;
-        for (int it = 0, i = lane; it < nit; it++, i += 32, q2 += 32) {
-            const unsigned b = __ballot_sync(FULL_MASK, i < L && *q2 > 2);
-            if (b) { if (leftPos == L) leftPos = it * 32 + __ffs(b) - 1; rightPos = it * 32 + 31 - __clz(b); }
-        }
-    }
-    const int wlo = REV ? leftPos : leftPos + 1, whi = REV ? rightPos - 1 : rightPos;
-    const uint32_t wspan = (whi >= wlo) ? (uint32_t)(whi - wlo) : 0u;
-    const int wlo_eff = (whi >= wlo) ? wlo : 0x7fffffff;
-    const uint32_t nsh = ((uint32_t)(c_s0 + lane) & 1u) ? 0u : 4u;     // nibble of this lane's bases (32*it is even: same parity every step)
-    const uint8_t* sp = seqp + ((c_s0 + (int)lane) >> 1);
-    const uint8_t* rp = ref + j0 + lane;
-    const uint32_t obs0 = S.obs + cov * (uint32_t)A.n_slots * row_bytes, mis0 = S.mis + cov * (uint32_t)A.n_slots * row_bytes;
-    int cidx4 = (cf + (int)lane * inc + Lc) * 4;                      // byte offset of the cycle cell inside a row
-    const int cstep4 = 128 * inc;
-    uint32_t next_code = ((int)lane < L) ? lds_u8(S.nib + ((*sp >> nsh) & 15u)) : 8u;
-    uint32_t prev_edge = 8;
-    uint32_t skipbits = 0;
-    if (n_skip | (flags & DF_SKIP_OVF)) {
-        for (int it = 0, i = lane; it < nit; it++, i += 32) {
-            bool sk1 = false;
-            if (n_skip) {
-                const uint32_t sk[4] = {d1.x, d1.y, d1.z, d1.w};
+// ---------------------------------------------------------------- kernel B: 16 consecutive bases per lane (the common case)
+// Reads whose clipped CIGAR is one M run (DF_LEAN, > 90 % of a WGS sample).  A warp takes 32 / lanes_per_read consecutive
+// reads per step; lane (r, c) owns bases [16c, 16c+16) of read r.  Everything per base is SIMD inside 32/64-bit words:
+//   QUAL    16 bytes  (unaligned 16-byte window out of two aligned 128-bit loads)
+//   SEQ     16 BAM nibbles -> base codes 0..3 / 8 by bit arithmetic, 4 bits per base
+//   REF     16 nibbles of pre-packed reference codes (pack_reference): mismatch = XOR
+//   context previous base in sequencing direction by shifting the code word one nibble (edge nibble from the neighbour lane)
+//   masks   counted / context-valid / mismatch / known-site flags as one bit per nibble
+// leaving ~14 instructions per base for the two shared-memory increments (cycle, context).  The cycle column of a
+// shared-memory row is skewed (cell c lives at c + c/16): the lanes of a read sit 16 cycles apart, which would otherwise
+// put them all on two banks.
+constexpr unsigned long long ONES = 0x1111111111111111ull;
+
+__device__ __forceinline__ void load16_unaligned(const uint8_t* p, uint32_t (&o)[4]) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint4* base = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
+    const uint4 A0 = __ldg(base), A1 = __ldg(base + 1);
+    const uint32_t off = (uint32_t)a & 15u;
+    uint32_t w0 = A0.x, w1 = A0.y, w2 = A0.z, w3 = A0.w, w4 = A1.x, w5 = A1.y;
+    if (off & 8) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = A1.z; w5 = A1.w; }
+    if (off & 4) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
+    const uint32_t sh = (off & 3) * 8;
+    o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh); o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
+}
+// 16 nibbles starting at nibble index `nidx` of a stream whose nibble 2b is the LOW nibble of byte b
+__device__ __forceinline__ unsigned long long load16_nibbles_le(const uint8_t* stream, uint64_t nidx) {
+    uint32_t o[4]; load16_unaligned(stream + (nidx >> 1), o);
+    const uint32_t sh = (uint32_t)(nidx & 1) * 4;
+    return (unsigned long long)__funnelshift_r(o[0], o[1], sh) | ((unsigned long long)__funnelshift_r(o[1], o[2], sh) << 32);
+}
+// the same for BAM SEQ (nibble 2b is the HIGH nibble of byte b)
+__device__ __forceinline__ unsigned long long load16_nibbles_bam(const uint8_t* stream, uint64_t nidx) {
+    uint32_t o[4]; load16_unaligned(stream + (nidx >> 1), o);
 #pragma unroll
-                for (int r = 0; r < 4; r++) if (r < (int)n_skip) sk1 |= ((uint32_t)i >= (sk[r] & 0xffff)) & ((uint32_t)i <= (sk[r] >> 16));
-            } else sk1 = (i < L) && ((A.ovf_bits[(size_t)d0.w * OVF_WORDS + (i >> 5)] >> (i & 31)) & 1);
-            skipbits |= (sk1 ? 1u : 0u) << it;
+    for (int k = 0; k < 3; k++) o[k] = ((o[k] & 0x0f0f0f0fu) << 4) | ((o[k] >> 4) & 0x0f0f0f0fu);
+    const uint32_t sh = (uint32_t)(nidx & 1) * 4;
+    return (unsigned long long)__funnelshift_r(o[0], o[1], sh) | ((unsigned long long)__funnelshift_r(o[1], o[2], sh) << 32);
+}
+// 8 BAM nibbles -> 8 base codes (A=1 C=2 G=4 T=8 -> 0..3, anything else -> 8)
+__device__ __forceinline__ uint32_t codes_of(uint32_t v) {
+    const uint32_t code = (((v >> 1) & 0x77777777u) - ((v >> 3) & 0x11111111u)) & 0x33333333u;
+    uint32_t pc = v - ((v >> 1) & 0x55555555u); pc = (pc & 0x33333333u) + ((pc >> 2) & 0x33333333u);   // bits set per nibble
+    const uint32_t t = pc ^ 0x11111111u;                         // zero iff exactly one bit
+    const uint32_t bad = (t | (t >> 1) | (t >> 2)) & 0x11111111u;
+    return (code & ~(bad * 7u)) | (bad << 3);
+}
+// one flag per nibble for the bases lo..hi (clamped to the 16 of a chunk)
+__device__ __forceinline__ unsigned long long range_flags(int lo, int hi) {
+    lo = max(lo, 0); hi = min(hi, CHUNK - 1);
+    if (lo > hi) return 0ull;
+    return (ONES << (4 * lo)) & (ONES >> (4 * (CHUNK - 1 - hi)));
+}
+
+struct ChunkSmem { uint32_t obs, mis, qslot; };   // shared-window byte addresses
+
+__global__ void __launch_bounds__(256, 4) bqsr_chunk_kernel(GatherArgs A) {
+    extern __shared__ uint32_t sm_tab[];
+    __shared__ int8_t sm_qslot[256];      // QUAL -> shared-memory slot; -1: counted but no slot (or QUAL > 93); -2: QUAL < 6, not counted
+    const unsigned lane = lane_id();
+    const int cells = A.geom.n_cov * A.n_slots * A.ncols_s;
+    uint32_t* sm_mis = sm_tab + cells;
+    for (int i = threadIdx.x; i < 2 * cells; i += blockDim.x) sm_tab[i] = 0;
+    { const int b = threadIdx.x; sm_qslot[b] = b < 6 ? (int8_t)-2 : (b < 94 ? A.qslot[b] : (int8_t)-1); }
+    __syncthreads();
+    ChunkSmem S;
+    S.obs = (uint32_t)__cvta_generic_to_shared(sm_tab); S.mis = (uint32_t)__cvta_generic_to_shared(sm_mis); S.qslot = (uint32_t)__cvta_generic_to_shared(sm_qslot);
+    const int Lc = A.Lc, lpr = A.lanes_per_read, rpw = 32 / lpr;
+    const uint32_t row_bytes = (uint32_t)A.ncols_s * 4u, ctx_off = (uint32_t)A.ctx_col_s * 4u;
+    const int r = (int)lane / lpr, c = (int)lane - r * lpr;                     // read slot inside the warp step, chunk inside the read
+    const bool lane_used = r < rpw;
+    const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5);
+    const uint64_t wid = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint4* dbase = reinterpret_cast<const uint4*>(A.desc);
+    uint32_t errbits = 0;
+    // descriptors are fetched one step ahead
+    uint64_t k = wid * rpw + (uint64_t)r;
+    uint4 nloc = make_uint4(0, 0, 0, 0), nsc = make_uint4(0, 0, 0, 0);
+    if (lane_used && k < A.n) { nloc = __ldg(dbase + 3 * k); nsc = __ldg(dbase + 3 * k + 1); }
+    for (uint64_t k0 = wid * rpw; k0 < A.n; k0 += warps * rpw) {
+        const uint4 loc = nloc, sc = nsc;
+        const uint64_t kcur = k0 + (uint64_t)r, knext = kcur + warps * rpw;
+        nloc = make_uint4(0, 0, 0, 0); nsc = nloc;
+        if (lane_used && knext < A.n) { nloc = __ldg(dbase + 3 * knext); nsc = __ldg(dbase + 3 * knext + 1); }
+        const uint32_t flags = sc.z & 0xff;
+        const int L = (lane_used && kcur < A.n && (flags & DF_LEAN)) ? (int)(sc.y >> 16) : 0;   // 0: nothing to do for this lane group
+        const int i0 = c * CHUNK, nb = min(max(L - i0, 0), CHUNK);                                // bases of this chunk
+        const bool rev = flags & DF_REVERSED;
+        // ---- loads ----
+        uint32_t Q[4] = {0, 0, 0, 0};
+        unsigned long long C = 0, R = 0;
+        if (nb > 0) {
+            const uint64_t qloc = ((uint64_t)loc.y << 32) | loc.x, nl = ((uint64_t)loc.w << 32) | loc.z;
+            const uint32_t refid = (uint32_t)(qloc >> 40);
+            load16_unaligned(A.qual + (qloc & ((1ull << 40) - 1)) + (uint64_t)i0, Q);
+            const unsigned long long nibs = load16_nibbles_bam(A.seq, nl + (uint64_t)i0);
+            R = load16_nibbles_le(A.refnib[refid], (uint64_t)((int64_t)(int32_t)sc.x - 1 + i0));
+            C = (unsigned long long)codes_of((uint32_t)nibs) | ((unsigned long long)codes_of((uint32_t)(nibs >> 32)) << 32);
+        }
+        const unsigned long long inlen = range_flags(0, nb - 1);
+        C = (C & (inlen * 15ull)) | ((ONES & ~inlen) << 3);                      // codes past the read end: 8
+        // ---- low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2 ----
+        int first = 0x7fffffff, last = -1;
+        {
+            unsigned long long g01 = 0, g23 = 0;   // bit 7 of each byte: QUAL > 2
+#pragma unroll
+            for (int wq = 0; wq < 4; wq++) {
+                const uint32_t v = Q[wq], f = (((v & 0x7f7f7f7fu) + 0x7d7d7d7du) | v) & 0x80808080u;
+                if (wq < 2) g01 |= (unsigned long long)f << (32 * wq); else g23 |= (unsigned long long)f << (32 * (wq - 2));
+            }
+            // bytes past the read end are zero only if nb == 0; mask them
+            if (nb < 8) { g23 = 0; g01 &= nb > 0 ? (~0ull >> (8 * (8 - nb))) : 0ull; } else if (nb < 16) g23 &= (nb > 8) ? (~0ull >> (8 * (16 - nb))) : 0ull;
+            if (g01) first = i0 + ((__ffsll((long long)g01) - 1) >> 3); else if (g23) first = i0 + 8 + ((__ffsll((long long)g23) - 1) >> 3);
+            if (g23) last = i0 + 8 + ((63 - __clzll((long long)g23)) >> 3); else if (g01) last = i0 + ((63 - __clzll((long long)g01)) >> 3);
+        }
+        // the lanes of one read reduce among themselves (segmented by member mask)
+        const unsigned gmask = lane_used ? ((lpr == 32 ? 0xffffffffu : ((1u << lpr) - 1u)) << (r * lpr)) : (1u << lane);
+        const int leftPos = __reduce_min_sync(gmask, first), rightPos = __reduce_max_sync(gmask, last);
+        // neighbour chunks' edge codes for the context of the first / last base of this chunk
+        const uint32_t c_hi = (uint32_t)(C >> 32), c_lo = (uint32_t)C;
+        uint32_t edge_prev = __shfl_up_sync(FULL_MASK, c_hi, 1) >> 28, edge_next = __shfl_down_sync(FULL_MASK, c_lo, 1) & 15u;
+        if (c == 0) edge_prev = 8; if (c == lpr - 1 || lane == 31) edge_next = 8;
+        if (L > 0) {   // (warp-level primitives are above this line)
+        // ---- per-base flags, one bit per nibble ----
+        const unsigned long long Pn = rev ? ((C >> 4) | ((unsigned long long)edge_next << 60)) : ((C << 4) | edge_prev);   // previous base in sequencing direction
+        const unsigned long long M3 = 0x3333333333333333ull, xr = rev ? M3 : 0ull;
+        const unsigned long long ctxw = ((Pn ^ xr) & M3) | (((C ^ xr) & M3) << 2);          // key>>4 = prev | cur<<2, complemented for reverse reads (bqsr.go:64-76)
+        const int wlo = rev ? leftPos : leftPos + 1, whi = rev ? rightPos - 1 : rightPos;      // bases whose context lies inside [leftPos, rightPos]
+        unsigned long long skipf = 0;
+        const uint32_t n_skip = (sc.z >> 16) & 0xff;
+        if (n_skip) {
+            const uint4 sk = __ldg(dbase + 3 * kcur + 2);
+            const uint32_t skv[4] = {sk.x, sk.y, sk.z, sk.w};
+#pragma unroll
+            for (int t = 0; t < 4; t++) if (t < (int)n_skip) skipf |= range_flags((int)(skv[t] & 0xffff) - i0, (int)(skv[t] >> 16) - i0);
+        }
+        const unsigned long long counted = ~(C >> 3) & ONES & ~skipf;                             // ACGT, inside the read, not a known site (QUAL >= 6 via the slot table)
+        const unsigned long long okc = counted & ~((Pn | C) >> 3) & range_flags(wlo - i0, whi - i0);
+        const unsigned long long X = C ^ R;
+        const unsigned long long snpf = (X | (X >> 1) | (X >> 2) | (X >> 3)) & counted;         // computeSnpEvents, bqsr.go:254-285
+        if (counted) {
+        // ---- table updates ----
+        const uint32_t cov = (sc.z >> 8) & 0xff;
+        const int lastf = (flags & DF_LAST) ? 1 : 0;
+        const int rof = 1 - 2 * lastf, inc = rev ? -rof : rof, cf = rof + (rev ? (L - 1) * rof : 0);   // prepareCycleCovariates, bqsr.go:376-383
+        const int ci0 = cf + i0 * inc + Lc;                                                          // cycle cell of the chunk's first base
+        const uint32_t obs0 = S.obs + cov * (uint32_t)A.n_slots * row_bytes;
+        unsigned long long later = snpf;                                                             // bases needing the slow tail: mismatches and slot-less QUAL
+        int ci = ci0;
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {
+            const uint32_t q = (Q[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            const int slot = lds_s8(S.qslot + q);
+            const bool cnt = (counted >> (4 * j)) & 1ull;
+            if (cnt && slot >= 0) {
+                const uint32_t orow = obs0 + (uint32_t)slot * row_bytes;
+                reds_inc(orow + (uint32_t)(ci + (ci >> 4)) * 4u);
+                if ((okc >> (4 * j)) & 1ull) reds_inc(orow + ctx_off + (uint32_t)((ctxw >> (4 * j)) & 15ull) * 4u);
+            }
+            if (cnt && slot == -1) later |= 1ull << (4 * j);
+            if (slot == -2) later &= ~(1ull << (4 * j));                                           // QUAL < 6: not counted at all
+            ci += inc;
+        }
+        while (later) {
+            const int j = (__ffsll((long long)later) - 1) >> 2;
+            later &= ~(15ull << (4 * j));
+            const uint32_t qw = j < 4 ? Q[0] : (j < 8 ? Q[1] : (j < 12 ? Q[2] : Q[3]));
+            const uint32_t q = (qw >> (8 * (j & 3))) & 0xffu;
+            const int slot = lds_s8(S.qslot + q);
+            const int cj = ci0 + j * inc;
+            const uint32_t ctx = (uint32_t)((ctxw >> (4 * j)) & 15ull);
+            const bool ok = (okc >> (4 * j)) & 1ull, snp = (snpf >> (4 * j)) & 1ull;
+            if (slot >= 0) {          // a mismatch (sparse, ~0.5 % of bases) on the CTA's second table
+                const uint32_t mrow = S.mis + (cov * (uint32_t)A.n_slots + (uint32_t)slot) * row_bytes;
+                reds_inc(mrow + (uint32_t)(cj + (cj >> 4)) * 4u);
+                if (ok) reds_inc(mrow + ctx_off + ctx * 4u);
+            } else count_rare(A, (int)cov, (int)q, cj - Lc, ctx, ok, snp ? 1u : 0u, false, &errbits);
+        }
+        }
         }
     }
-    int i = lane;
-#pragma unroll 1
-    for (int it = 0; it < nit; it++) {
-        const uint32_t code = next_code;
-        sp += 16;
-        next_code = (i + 32 < L) ? lds_u8(S.nib + ((*sp >> nsh) & 15u)) : 8u;
-        const uint32_t q = (i < L) ? (uint32_t)*qp : 0u;
-        const uint32_t rb = (i < nref) ? (uint32_t)*rp : 0xffu;
-        qp += 32; rp += 32;
-        uint32_t pcode;
-        if (REV) { pcode = __shfl_sync(FULL_MASK, code, (lane + 1) & 31); const uint32_t e = __shfl_sync(FULL_MASK, next_code, 0); if (lane == 31) pcode = e; }
-        else { pcode = __shfl_sync(FULL_MASK, code, (lane - 1) & 31); if (lane == 0) pcode = prev_edge; prev_edge = __shfl_sync(FULL_MASK, code, 31); }
-        const bool counted = (code < 8u) & (q >= 6u) & !((skipbits >> it) & 1u);      // bqsr.go:506-515 (code is 8 beyond L)
-        const int slot = (i < nref) ? lds_s8(S.qslot + q) : -1;                            // -1: no slot, QUAL > 93, or past the contig end
-        const uint32_t snp = lds_u8(S.refcode + rb) != code;
-        const bool okc = (pcode < 8u) & ((uint32_t)(i - wlo_eff) <= wspan);
-        const uint32_t ctx = REV ? ((pcode ^ 3u) | ((code ^ 3u) << 2)) : (pcode | (code << 2));   // key>>4 = prev | cur<<2 (bqsr.go:64-76)
-        if (counted) {
-            if (slot >= 0) {
-                const uint32_t orow = obs0 + (uint32_t)slot * row_bytes;
-                reds_inc(orow + (uint32_t)cidx4);
-                if (okc) reds_inc(orow + ctx_off_bytes + ctx * 4u);
-                if (snp) {   // mismatches are sparse (~0.5 % of bases)
-                    const uint32_t mrow = mis0 + (uint32_t)slot * row_bytes;
-                    reds_inc(mrow + (uint32_t)cidx4);
-                    if (okc) reds_inc(mrow + ctx_off_bytes + ctx * 4u);
-                }
-            } else count_rare(A, (int)cov, (int)q, (cidx4 >> 2) - Lc, ctx, okc, snp, i >= nref, errbits);
-        }
-        cidx4 += cstep4; i += 32;
+    errbits = __reduce_or_sync(FULL_MASK, errbits);
+    if (errbits && lane == 0) atomicOr(A.err, errbits);
+    __syncthreads();
+    const int ncols_s = A.ncols_s, ctx_col = A.ctx_col_s;
+    for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+        const uint32_t v = sm_tab[i], e = sm_mis[i];
+        if (!(v | e)) continue;
+        const int col_s = i % ncols_s, cs = i / ncols_s, slot = cs % A.n_slots, cov = cs / A.n_slots;
+        int col_g;
+        if (col_s < ctx_col) { const int cyc_cell = 16 * (col_s / 17) + col_s % 17; col_g = A.geom.col_cycle(cyc_cell - Lc); }   // undo the skew
+        else col_g = A.geom.col_ctx(col_s - ctx_col);
+        if (v) atomicAdd(A.tables + 2 * A.geom.idx(cov, A.slot_q[slot], col_g), (unsigned long long)v);
+        if (e) atomicAdd(A.tables + 2 * A.geom.idx(cov, A.slot_q[slot], col_g) + 1, (unsigned long long)e);
     }
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2048 / (WARPS_PER_BLOCK * 32 * 2)) bqsr_count_kernel(GatherArgs A) {
+// reference bases -> 4-bit codes (baseToIntMap, bqsr.go:247-252: A/a/* C/c G/g T/t -> 0..3, everything else 8), low nibble first
+__global__ void __launch_bounds__(256) ref_pack_kernel(const uint8_t* __restrict__ ref, uint64_t n, uint8_t* __restrict__ out, uint64_t n_out) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_out) return;
+    uint32_t v = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint64_t j = 2 * t + h; uint32_t cd = 8;
+        if (j < n) { const uint8_t b = ref[j]; if (b == 'A' || b == 'a' || b == '*') cd = 0; else if (b == 'C' || b == 'c') cd = 1; else if (b == 'G' || b == 'g') cd = 2; else if (b == 'T' || b == 't') cd = 3; }
+        v |= cd << (4 * h);
+    }
+    out[t] = (uint8_t)v;
+}
+
+// reads for the general kernel: eligible (c_len > 0) but not DF_LEAN
+__global__ void __launch_bounds__(256) gen_list_kernel(GatherArgs A) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool g = false;
+    if (k < A.n) { const uint4 sc = __ldg(reinterpret_cast<const uint4*>(A.desc) + 3 * k + 1); g = (sc.y >> 16) != 0 && !(sc.z & DF_LEAN); }
+    const unsigned b = __ballot_sync(FULL_MASK, g);
+    if (!b) return;
+    uint32_t base = 0;
+    if (lane_id() == 0) base = atomicAdd(A.gen_count, (uint32_t)__popc(b));
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (g) A.gen_list[base + __popc(b & lanemask_lt())] = (uint32_t)k;
+}
+
+// ---------------------------------------------------------------- kernel C: one warp per read, one lane per base
+// (insertions / deletions, cycles beyond --max-cycle, > 4 known-site ranges, reads running off their contig)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2048 / (WARPS_PER_BLOCK * 32 * 2)) bqsr_general_kernel(GatherArgs A, uint32_t n_gen) {
     extern __shared__ uint32_t sm_tab[];
     __shared__ uint8_t sm_refcode[256];   // baseToIntMap (bqsr.go:247-252): A/a/* C/c G/g T/t -> 0..3, everything else 8
     __shared__ int8_t sm_qslot[256];      // QUAL -> shared-memory slot, -1 = none (and for QUAL > 93)
-    __shared__ uint8_t sm_nib[16];        // BAM nibble -> A C G T = 0..3, everything else 8
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
-    const int cells = A.geom.n_cov * A.n_slots * A.ncols_s;
+    const int Lc = A.Lc, ncols_s = 2 * Lc + 1 + 16, max_cycle = A.geom.max_cycle;    // this kernel's rows are not skewed
+    const int cells = A.geom.n_cov * A.n_slots * ncols_s;
     uint32_t* sm_mis = sm_tab + cells;
     for (int i = threadIdx.x; i < 2 * cells; i += blockDim.x) sm_tab[i] = 0;
     {
@@ -415,43 +573,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2048 / (WARPS_PER_BLOCK 
         if (b == 'A' || b == 'a' || b == '*') c = 0; else if (b == 'C' || b == 'c') c = 1; else if (b == 'G' || b == 'g') c = 2; else if (b == 'T' || b == 't') c = 3;
         sm_refcode[b] = c;
         sm_qslot[b] = b < 94 ? A.qslot[b] : (int8_t)-1;
-        if (b < 16) sm_nib[b] = (uint8_t)nib_code((uint32_t)b);
     }
     __syncthreads();
-    const int Lc = A.Lc, ncols_s = A.ncols_s, max_cycle = A.geom.max_cycle;
-    LeanSmem LS;
-    LS.obs = (uint32_t)__cvta_generic_to_shared(sm_tab); LS.mis = (uint32_t)__cvta_generic_to_shared(sm_mis);
-    LS.refcode = (uint32_t)__cvta_generic_to_shared(sm_refcode); LS.qslot = (uint32_t)__cvta_generic_to_shared(sm_qslot); LS.nib = (uint32_t)__cvta_generic_to_shared(sm_nib);
-    // The per-read critical path is a chain of dependent DRAM accesses (descriptor -> offsets -> strips); with ~32 resident
-    // warps per SM that latency, not the instruction count, bounds the kernel.  So the chain is software pipelined across
-    // reads WITHOUT holding data in registers: while read k is processed, the scalars of read k+2W are requested and the
-    // cache lines of read k+W (QUAL, SEQ, reference window) are pulled into L1 with prefetch instructions.
     const uint64_t stride = (uint64_t)gridDim.x * WARPS_PER_BLOCK;
-    uint64_t kk = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + w;
-    uint4 pd0 = make_uint4(0, 0, 0, 0); uint64_t pqo = 0, pso = 0; int32_t prid = 0;     // scalars of the NEXT read (k + W)
-    if (kk + stride < A.n) { pd0 = *reinterpret_cast<const uint4*>(A.desc + kk + stride); pqo = A.qual_off[kk + stride]; pso = A.seq_off[kk + stride]; prid = A.refid[kk + stride]; }
-    for (uint64_t k = kk; k < A.n; k += stride) {
-        // request the scalars of read k + 2W (consumed at the end of this iteration)
-        uint4 nd0 = make_uint4(0, 0, 0, 0); uint64_t nqo = 0, nso = 0; int32_t nrid = 0;
-        if (k + 2 * stride < A.n) { nd0 = *reinterpret_cast<const uint4*>(A.desc + k + 2 * stride); nqo = A.qual_off[k + 2 * stride]; nso = A.seq_off[k + 2 * stride]; nrid = A.refid[k + 2 * stride]; }
-        // pull the lines of read k + W towards L1: lanes 0..7 cover <= 8 lines (QUAL 3, SEQ 2, reference 3 for 192 bases)
-        {
-            const int pL = (int)(pd0.y >> 16), pc0 = (int)(pd0.y & 0xffff);
-            if (pL > 0) {
-                const uint8_t* pq = A.qual + pqo + pc0; const uint8_t* ps = A.seq + pso + (pc0 >> 1);
-                const uint8_t* pr = A.ref[prid] + ((int64_t)(int32_t)pd0.x - 1);
-                const uint8_t* ptr = nullptr;
-                if (lane < 3) { if ((int)lane * 128 < pL + 127) ptr = pq + lane * 128; }
-                else if (lane < 5) { if ((int)(lane - 3) * 128 < (pL >> 1) + 127) ptr = ps + (lane - 3) * 128; }
-                else if (lane < 8) { if ((int)(lane - 5) * 128 < pL + 127) ptr = pr + (lane - 5) * 128; }
-                if (ptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr));
-            }
-        }
-        // descriptor: two 16-byte loads, broadcast to the warp
-        const uint4 d0 = *reinterpret_cast<const uint4*>(A.desc + k);
+    for (uint64_t gi = (uint64_t)blockIdx.x * WARPS_PER_BLOCK + w; gi < n_gen; gi += stride) {
+        const uint64_t k = A.gen_list[gi];
+        const uint4* dp = reinterpret_cast<const uint4*>(A.desc) + 3 * k;
+        const uint4 d0 = __ldg(dp + 1);
         const int L = (int)(d0.y >> 16);
-        if (L == 0) { pd0 = nd0; pqo = nqo; pso = nso; prid = nrid; continue; }
-        const uint4 d1 = *(reinterpret_cast<const uint4*>(A.desc + k) + 1);
+        if (L == 0) continue;
+        const uint4 d1 = __ldg(dp + 2);
         const int c_pos = (int)d0.x, c_s0 = (int)(d0.y & 0xffff);
         const uint32_t flags = d0.z & 0xff, cov = (d0.z >> 8) & 0xff, n_skip = (d0.z >> 16) & 0xff;
         const int reversed = (flags & DF_REVERSED) ? 1 : 0, last = (flags & DF_LAST) ? 1 : 0;
@@ -459,20 +590,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2048 / (WARPS_PER_BLOCK 
         const uint8_t* qualp = A.qual + A.qual_off[k] + c_s0;
         const uint8_t* seqp = A.seq + A.seq_off[k];
         const uint8_t* ref = A.ref[refid]; const int64_t reflen = (int64_t)A.ref_len[refid];
-        pd0 = nd0; pqo = nqo; pso = nso; prid = nrid;     // (the `continue`s below must not skip this hand-over)
         const int nit = (L + 31) >> 5;
-        {
-            // common case: single M operation and all cycles within --max-cycle -> lean path
-            const int rof_ = 1 - 2 * last, ca = rof_ + reversed * (L - 1) * rof_, cb = ca + (L - 1) * (1 - 2 * reversed) * rof_;
-            if ((flags & DF_SINGLE_M) && max(ca, cb) <= max_cycle && min(ca, cb) >= -max_cycle) {
-                uint32_t eb = 0;
-                if (reversed) count_read_lean<true>(A, LS, (uint32_t)ncols_s * 4u, (uint32_t)(2 * Lc + 1) * 4u, Lc, d0, d1, qualp, seqp, ref, reflen, lane, &eb);
-                else count_read_lean<false>(A, LS, (uint32_t)ncols_s * 4u, (uint32_t)(2 * Lc + 1) * 4u, Lc, d0, d1, qualp, seqp, ref, reflen, lane, &eb);
-                eb = __reduce_or_sync(FULL_MASK, eb);
-                if (eb && lane == 0) atomicOr(A.err, eb);
-                continue;
-            }
-        }
         // ---- general path: insertions / deletions, or a cycle beyond --max-cycle somewhere in the read ----
         // low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2
         int leftPos = L, rightPos = -1;
@@ -607,6 +725,22 @@ __global__ void derive_q_kernel(TableGeom geom, long long* tables) {
 
 }  // namespace
 
+// nibble-packed reference codes of one contig (read by the chunk kernel); 32 bytes of padding on both sides because the
+// kernel reads aligned 16-byte windows around the bases it needs
+int pack_reference(elp_ctx* c, int contig) {
+    const uint64_t n = c->ref_len[contig], n_out = (n + 1) / 2;
+    if (c->d_refnib_raw[contig]) { cudaFree(c->d_refnib_raw[contig]); c->d_refnib_raw[contig] = nullptr; }
+    CUDA_TRY(c, cudaMalloc(&c->d_refnib_raw[contig], n_out + 64));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_refnib_raw[contig], 0x88, n_out + 64, c->stream));
+    if (n_out) {
+        c->launches++;
+        ref_pack_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(c->d_ref[contig], n, c->d_refnib_raw[contig] + 32, n_out);
+        LAUNCH_CHECK(c);
+    }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return E_OK;
+}
+
 int phase_bqsr_gather(elp_ctx* c) {
     if (!c->sorted) return c->fail(E_STATE, "elp_bqsr_gather called before elp_sort_markdup");
     int rc = upload_side_inputs(c);
@@ -629,7 +763,9 @@ int phase_bqsr_gather(elp_ctx* c) {
         const double bytes = (double)n * (19 + 4 + 8 + 8) + (double)c->n_cigar * 4 + (double)c->n_seq + (double)c->n_qual + (double)ref_bytes;
         // slot map: the most frequent QUAL values >= 6 of a sample get shared-memory counters (<= 48 KB per CTA)
         const int Lc = std::max(1, std::min(c->max_cycle, c->h_ranges.lseq_max));
-        A.Lc = Lc; A.ncols_s = 2 * Lc + 1 + 16;
+        A.Lc = Lc; A.ctx_col_s = 2 * Lc + ((2 * Lc) >> 4) + 1; A.ncols_s = A.ctx_col_s + 16;
+        A.lanes_per_read = std::min(32, std::max(1, (c->h_ranges.lseq_max + CHUNK - 1) / CHUNK));
+        A.refnib = c->d_refnib_ptrs;
         for (int q = 0; q < 94; q++) { A.qslot[q] = -1; A.slot_q[q] = 0; }
         {
             CUDA_TRY(c, c->scan_tmp.reserve(256 + 4, c->stream));
@@ -652,22 +788,40 @@ int phase_bqsr_gather(elp_ctx* c) {
         const size_t smem = (size_t)c->geom.n_cov * A.n_slots * A.ncols_s * 4 * 2;
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         // descriptors (32 B/read) and the overflow skip bitmasks live in scratch buffers that are free in this phase
-        CUDA_TRY(c, c->keys_a.reserve(n * 4 + 8, c->stream));
+        CUDA_TRY(c, c->keys_a.reserve(n * 6 + 8, c->stream));
+        CUDA_TRY(c, c->vals_b.reserve(n + 8, c->stream));
+        A.gen_list = c->vals_b.p;
         A.desc = reinterpret_cast<ReadDesc*>(c->keys_a.p);
         A.ovf_cap = (uint32_t)std::min<uint64_t>(n, (n >> 4) + 4096);
         CUDA_TRY(c, c->vals_a.reserve((size_t)A.ovf_cap * OVF_WORDS + 8, c->stream));
         A.ovf_bits = c->vals_a.p;
-        A.ovf_count = c->scan_tmp.p;   // one u32, zeroed below
-        CUDA_TRY(c, cudaMemsetAsync(A.ovf_count, 0, 4, c->stream));
-        c->begin("bqsr_prep", (double)n * (4 * 7 + 2 + 1 + 8 + 4 + 32) + (double)c->n_cigar * 4);
+        A.ovf_count = c->scan_tmp.p;   // two u32 (overflow slots, general-kernel reads), zeroed below
+        A.gen_count = c->scan_tmp.p + 1;
+        CUDA_TRY(c, cudaMemsetAsync(A.ovf_count, 0, 8, c->stream));
+        c->begin("bqsr_prep", (double)n * (4 * 7 + 2 + 1 + 8 + 8 + 4 + 48) + (double)c->n_cigar * 4);
         bqsr_prep_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(A);
         c->end(); LAUNCH_CHECK(c);
-        uint64_t grid = std::min<uint64_t>((n + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (uint64_t)sms * 4);
-        grid = std::max<uint64_t>(grid, (n + (4u << 20) - 1) / (4u << 20));   // <= 4 M reads per CTA keeps the 32-bit shared counters far from overflow
-        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-        c->begin("bqsr_gather", bytes);
-        bqsr_count_kernel<<<(unsigned)grid, WARPS_PER_BLOCK * 32, smem, c->stream>>>(A);
+        c->begin("bqsr_gen_list", (double)n * 20);
+        gen_list_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(A);
         c->end(); LAUNCH_CHECK(c);
+        const uint64_t rpw = 32 / A.lanes_per_read, steps = (n + rpw - 1) / rpw;
+        uint64_t grid = std::min<uint64_t>((steps + 7) / 8, (uint64_t)sms * 4);
+        grid = std::max<uint64_t>(grid, (n + (4u << 20) - 1) / (4u << 20));   // <= 4 M reads per CTA keeps the 32-bit shared counters far from overflow
+        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        c->begin("bqsr_gather", bytes);
+        bqsr_chunk_kernel<<<(unsigned)grid, 256, smem, c->stream>>>(A);
+        c->end(); LAUNCH_CHECK(c);
+        uint32_t n_gen = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&n_gen, A.gen_count, 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        if (n_gen) {
+            const size_t smem_g = (size_t)c->geom.n_cov * A.n_slots * (2 * Lc + 1 + 16) * 4 * 2;
+            const uint64_t grid_g = std::min<uint64_t>(((uint64_t)n_gen + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (uint64_t)sms * 4);
+            CUDA_TRY(c, cudaFuncSetAttribute(bqsr_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_g, 1024)));
+            c->begin("bqsr_gather_general", (double)n_gen * (48 + 19 + 225 + 150));
+            bqsr_general_kernel<<<(unsigned)grid_g, WARPS_PER_BLOCK * 32, smem_g, c->stream>>>(A, n_gen);
+            c->end(); LAUNCH_CHECK(c);
+        }
     }
     c->begin("bqsr_derive_q", 0);
     derive_q_kernel<<<c->geom.n_cov * 94, 256, 0, c->stream>>>(c->geom, reinterpret_cast<long long*>(c->d_tables));

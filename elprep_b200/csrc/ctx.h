@@ -77,6 +77,8 @@ struct elp_ctx {
     std::vector<uint8_t*> d_ref;          // per contig
     std::vector<uint64_t> ref_len;
     const uint8_t** d_ref_ptrs = nullptr; // [n_contigs] device array of pointers
+    std::vector<uint8_t*> d_refnib_raw;   // per contig: 4-bit reference codes (bqsr_gather.cu pack_reference), payload at +32
+    const uint8_t** d_refnib_ptrs = nullptr;
     uint64_t* d_ref_len = nullptr;
     std::vector<int32_t*> d_sites;        // per contig, (start,end) pairs
     std::vector<uint64_t> n_sites;
@@ -200,4 +202,5 @@ int phase_bqsr_gather(elp_ctx* c);
 int phase_bqsr_finalize(elp_ctx* c, const char* report_path);
 int phase_bqsr_apply(elp_ctx* c);
 int upload_side_inputs(elp_ctx* c);
+int pack_reference(elp_ctx* c, int contig);
 int check_device_errors(elp_ctx* c);
