@@ -5,25 +5,21 @@
 // :973-1000).  The result is written as a contiguous QUAL stream in output order (what elp_fetch copies back); the
 // original QUAL arena stays untouched.
 //
-// Kernel shape (the kernel was instruction-issue bound with one base per lane): 8 lanes per read, 4 reads per warp.
-//   1. the group's 8 lanes copy the read's QUAL and SEQ strips into shared memory with aligned 16-byte loads
-//      (the strips sit at arbitrary byte offsets of the arenas, so the aligned window around them is staged) and find the
-//      low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331) on the fly with SIMD byte compares;
-//   2. every lane walks ~L/8 CONSECUTIVE bases out of shared memory: the previous base of the 2-mer context is simply
-//      the last one it saw, the cycle advances by +-1, the LUT address by +-17;
-//   3. the strip is written back as 16-byte stores aligned on the OUTPUT stream (funnel-shifted out of shared memory);
-//      only the first/last partial chunk of a read uses byte stores.
+// Kernel shape (same decomposition as the gather's chunk kernel, bqsr_gather.cu): a lane owns 16 consecutive bases of a
+// read, a warp takes 32 / lanes_per_read reads.
+//   1. 16 QUAL bytes and 16 SEQ nibbles come out of aligned 128-bit loads (funnel-shifted to the read's byte offset);
+//      base codes, the 2-mer context of every base and the low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331)
+//      are computed word-parallel; the tails are reduced across the lanes of the read with member-mask reductions;
+//   2. per base: one byte load from the LUT (L1/L2 resident) and a byte insert; cycle advances by +-1, LUT address by +-17;
+//   3. the lanes park their 16 result bytes in shared memory and the read's strip is written as 16-byte stores aligned
+//      on the OUTPUT stream (funnel-shifted out of shared memory); only the partial chunks at the ends use byte stores.
 // With lut == nullptr the kernel only materialises the output-order QUAL stream (no BQSR requested).
 #include "ctx.h"
+#include "bqsr_simd.cuh"
 
 namespace {
 
-constexpr int G = 8;                    // lanes per read
-constexpr int RPW = 32 / G;             // reads per warp
 constexpr int WARPS = 8;
-constexpr int MAXL = 512;               // longest read handled (cycles beyond --max-cycle 500 are an error anyway)
-constexpr int QSTRIP = MAXL + 48;       // staged QUAL window: <= 15 bytes of lead-in + L + padding, multiple of 16
-constexpr int SSTRIP = MAXL / 2 + 48;
 
 struct ApplyArgs {
     uint64_t n;
@@ -31,6 +27,7 @@ struct ApplyArgs {
     const uint8_t *seq, *qual; uint8_t* out;
     const int32_t* rg_cov; int n_rg; const uint8_t* cov_exists;
     const uint8_t* lut; int lut_maxcyc, max_cycle;
+    int lanes_per_read;
     uint32_t* err;
 };
 
@@ -44,14 +41,16 @@ __device__ __forceinline__ uint32_t lds_unaligned32(const uint8_t* p) {   // 4 b
 }
 
 __global__ void __launch_bounds__(WARPS * 32) bqsr_apply_kernel(ApplyArgs A) {
-    __shared__ __align__(16) uint8_t sm_q[WARPS][RPW][QSTRIP];
-    __shared__ __align__(16) uint8_t sm_s[WARPS][RPW][SSTRIP];
-    const unsigned lane = lane_id(), w = threadIdx.x >> 5, sub = lane & (G - 1), grp = lane / G;
-    const uint64_t k = ((uint64_t)blockIdx.x * WARPS + w) * RPW + grp;
-    const bool valid = k < A.n;
+    __shared__ __align__(16) uint8_t sm_o[WARPS][32 * CHUNK + 16];   // one 16-byte cell per lane; the cells of a read are contiguous
+    const unsigned lane = lane_id(), w = threadIdx.x >> 5;
+    const int lpr = A.lanes_per_read, rpw = 32 / lpr;
+    const int r = (int)lane / lpr, c = (int)lane - r * lpr;
+    const bool lane_used = r < rpw;
+    const uint64_t k = ((uint64_t)blockIdx.x * WARPS + w) * (uint64_t)rpw + (uint64_t)r;
+    const bool valid = lane_used && k < A.n;
     int L = valid ? A.lseq[k] : 0;
     uint32_t errbits = 0;
-    if (L > MAXL) { errbits |= DERR_READLEN_LIMIT; L = 0; }
+    if (L > CHUNK * lpr) { errbits |= DERR_READLEN_LIMIT; L = 0; }
     const uint64_t qoff = valid ? A.qual_off[k] : 0, ooff = valid ? A.out_off[k] : 0;
     bool recal = valid && A.lut != nullptr && L > 0;
     int cov = 0;
@@ -60,91 +59,73 @@ __global__ void __launch_bounds__(WARPS * 32) bqsr_apply_kernel(ApplyArgs A) {
         if (g < 0 || g >= A.n_rg) { errbits |= DERR_NORG; recal = false; }                 // readGroupCovariate panics, bqsr.go:38
         else { cov = A.rg_cov[g]; if (!A.cov_exists[cov]) recal = false; }                  // no recalibration, bqsr table empty (:950-953)
     }
-    uint8_t* sq = sm_q[w][grp];
-    uint8_t* ss = sm_s[w][grp];
-    // ---- 1. stage the strips (aligned 16-byte windows) and find the low-quality tails ----
-    const uint32_t qsh = (uint32_t)(qoff & 15);
-    int leftPos = L, rightPos = -1;
-    if (L > 0) {
-        const uint64_t qa = qoff & ~15ull;
-        const int nqc = (int)((qsh + (uint32_t)L + 15u) >> 4);
-        for (int c = sub; c < nqc; c += G) {
-            const uint4 v = ld_stream_u4(A.qual + qa + 16ull * c);
-            *reinterpret_cast<uint4*>(sq + 16 * c) = v;
-            if (recal) {
-                const uint32_t wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    uint32_t m = __vcmpgtu4(wd[t], 0x02020202u);                           // 0xff per byte with QUAL > 2
-                    const int r0 = 16 * c + 4 * t - (int)qsh;                               // read coordinate of byte 0 of this word
-                    if (r0 < 0) m &= (r0 <= -4) ? 0u : (0xffffffffu << (8 * (-r0)));
-                    if (r0 + 4 > L) m &= (r0 >= L) ? 0u : (0xffffffffu >> (8 * (r0 + 4 - L)));
-                    if (m) { leftPos = min(leftPos, r0 + ((__ffs(m) - 1) >> 3)); rightPos = max(rightPos, r0 + ((31 - __clz(m)) >> 3)); }
-                }
-            }
+    const int i0 = c * CHUNK, nb = min(max(L - i0, 0), CHUNK);
+    // ---- 1. loads and word-parallel covariates ----
+    uint32_t Q[4] = {0, 0, 0, 0};
+    unsigned long long C = 0;
+    if (nb > 0) {
+        load16_unaligned(A.qual + qoff + (uint64_t)i0, Q);
+        if (recal) {
+            const unsigned long long nibs = load16_nibbles_bam(A.seq, A.seq_off[k] * 2 + (uint64_t)i0);
+            C = (unsigned long long)codes_of((uint32_t)nibs) | ((unsigned long long)codes_of((uint32_t)(nibs >> 32)) << 32);
         }
     }
-    uint32_t ssh = 0;
-    if (recal) {
-        const uint64_t soff = A.seq_off[k];
-        ssh = (uint32_t)(soff & 15);
-        const uint64_t sa = soff & ~15ull;
-        const int nsc = (int)((ssh + (uint32_t)((L + 1) >> 1) + 15u) >> 4);
-        for (int c = sub; c < nsc; c += G) *reinterpret_cast<uint4*>(ss + 16 * c) = ld_stream_u4(A.seq + sa + 16ull * c);
-    }
-#pragma unroll
-    for (int o = 1; o < G; o <<= 1) { leftPos = min(leftPos, __shfl_xor_sync(FULL_MASK, leftPos, o)); rightPos = max(rightPos, __shfl_xor_sync(FULL_MASK, rightPos, o)); }
-    __syncwarp();
-    // ---- 2. every lane recalibrates a run of consecutive bases in place ----
-    if (recal) {
+    const unsigned long long inlen = range_flags(0, nb - 1);
+    C = (C & (inlen * 15ull)) | ((ONES & ~inlen) << 3);                          // codes past the read end: 8
+    int first, last;
+    qual_gt2_span(Q, nb, i0, first, last);
+    const unsigned gmask = lane_used ? ((lpr == 32 ? 0xffffffffu : ((1u << lpr) - 1u)) << (r * lpr)) : (1u << lane);
+    const int leftPos = __reduce_min_sync(gmask, first), rightPos = __reduce_max_sync(gmask, last);
+    const uint32_t c_hi = (uint32_t)(C >> 32), c_lo = (uint32_t)C;
+    uint32_t edge_prev = __shfl_up_sync(FULL_MASK, c_hi, 1) >> 28, edge_next = __shfl_down_sync(FULL_MASK, c_lo, 1) & 15u;
+    if (c == 0) edge_prev = 8;
+    if (c == lpr - 1 || lane == 31) edge_next = 8;
+    // ---- 2. LUT lookups ----
+    if (recal && nb > 0) {
         const uint16_t f = A.flag[k];
-        const int reversed = (f & F_REVERSED) ? 1 : 0, last = (f & F_LAST) ? 1 : 0;
-        const int rof = 1 - 2 * last, cf = rof + reversed * (L - 1) * rof, inc = (1 - 2 * reversed) * rof;   // prepareCycleCovariates, bqsr.go:376-383
+        const bool rev = f & F_REVERSED;
+        const int lastf = (f & F_LAST) ? 1 : 0;
+        const int rof = 1 - 2 * lastf, inc = rev ? -rof : rof, cf = rof + (rev ? (L - 1) * rof : 0);   // prepareCycleCovariates, bqsr.go:376-383 (full read length)
+        const unsigned long long Pn = rev ? ((C >> 4) | ((unsigned long long)edge_next << 60)) : ((C << 4) | edge_prev);
+        const unsigned long long M3 = 0x3333333333333333ull, xr = rev ? M3 : 0ull;
+        const unsigned long long ctxw = ((Pn ^ xr) & M3) | (((C ^ xr) & M3) << 2);          // key>>4 = prev | cur<<2, complemented for reverse reads
+        const int wlo = rev ? leftPos : leftPos + 1, whi = rev ? rightPos - 1 : rightPos;      // low-quality tails read as N
+        const unsigned long long okc = ~((Pn | C) >> 3) & ONES & range_flags(wlo - i0, whi - i0);
         const uint32_t ncyc17 = (2u * (uint32_t)A.lut_maxcyc + 1u) * 17u;
         const uint8_t* lut_cov = A.lut + (size_t)cov * 94u * ncyc17;
-        const int C = (L + G - 1) / G, c0 = sub * C, c1 = min(L, c0 + C);
-        const uint8_t* sb = ss + ssh;
-        uint8_t* qb = sq + qsh;
-        auto base_idx = [&](int i) -> int { const uint32_t b = sb[i >> 1]; const uint32_t nb = (i & 1) ? (b & 15u) : (b >> 4); return (__popc(nb) == 1) ? (__ffs(nb) - 1) : -1; };
-        // neighbour in sequencing direction: previous read index for forward reads, next for reverse reads; bases outside
-        // [leftPos, rightPos] read as N (low-quality tails)
-        int cur = (c0 < c1) ? base_idx(c0) : -1;
-        int nbr = -1;
-        if (!reversed && c0 >= 1 && c0 < c1) nbr = base_idx(c0 - 1);
-        for (int i = c0; i < c1; i++) {
-            int nxt = -1;
-            if (i + 1 < L) nxt = base_idx(i + 1);
-            const uint32_t q = qb[i];
-            if (q >= 6) {                                                                   // minInterestingQual
-                const int cyc = cf + i * inc;
+        int cyc = cf + i0 * inc;
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {
+            const uint32_t q = (Q[j >> 2] >> (8 * (j & 3))) & 0xffu;
+            if (j < nb && q >= 6) {                                                         // minInterestingQual
                 if (q > 93) errbits |= DERR_QUAL_RANGE;
                 else if (cyc > A.max_cycle || cyc < -A.max_cycle) errbits |= DERR_CYCLE;   // checkCycleCovariate :364-369
                 else {
-                    uint32_t ctx = 16;                                                      // 16 = no context (key -1)
-                    if (!reversed) { if (cur >= 0 && nbr >= 0 && i - 1 >= leftPos && i <= rightPos) ctx = (uint32_t)(nbr | (cur << 2)); }
-                    else { if (cur >= 0 && nxt >= 0 && i >= leftPos && i + 1 <= rightPos) ctx = (uint32_t)((3 - nxt) | ((3 - cur) << 2)); }
-                    qb[i] = lut_cov[q * ncyc17 + (uint32_t)(cyc + A.lut_maxcyc) * 17u + ctx];
+                    const uint32_t ctx = ((okc >> (4 * j)) & 1ull) ? (uint32_t)((ctxw >> (4 * j)) & 15ull) : 16u;   // 16 = no context (key -1)
+                    const uint32_t v = __ldg(lut_cov + q * ncyc17 + (uint32_t)(cyc + A.lut_maxcyc) * 17u + ctx);
+                    Q[j >> 2] = (Q[j >> 2] & ~(0xffu << (8 * (j & 3)))) | (v << (8 * (j & 3)));
                 }
             }
-            nbr = cur; cur = nxt;
+            cyc += inc;
         }
     }
+    *reinterpret_cast<uint4*>(&sm_o[w][lane * CHUNK]) = make_uint4(Q[0], Q[1], Q[2], Q[3]);
     __syncwarp();
     // ---- 3. write the strip in 16-byte chunks aligned on the output stream ----
     if (L > 0) {
         const uint32_t osh = (uint32_t)(ooff & 15);
         const uint64_t oa = ooff & ~15ull;
         const int noc = (int)((osh + (uint32_t)L + 15u) >> 4);
-        const uint8_t* src = sq + qsh;
-        for (int c = sub; c < noc; c += G) {
-            const int r0 = 16 * c - (int)osh;                                               // read coordinate of the chunk's first byte
+        const uint8_t* src = &sm_o[w][r * lpr * CHUNK];
+        for (int cc = c; cc < noc; cc += lpr) {
+            const int r0 = 16 * cc - (int)osh;                                              // read coordinate of the chunk's first byte
             if (r0 >= 0 && r0 + 16 <= L) {
                 uint4 v;
                 v.x = lds_unaligned32(src + r0); v.y = lds_unaligned32(src + r0 + 4); v.z = lds_unaligned32(src + r0 + 8); v.w = lds_unaligned32(src + r0 + 12);
-                *reinterpret_cast<uint4*>(A.out + oa + 16ull * c) = v;
+                *reinterpret_cast<uint4*>(A.out + oa + 16ull * cc) = v;
             } else {
                 const int lo = max(r0, 0), hi = min(r0 + 16, L);                            // partial chunk shared with the neighbouring read
-                for (int r = lo; r < hi; r++) A.out[ooff + r] = src[r];
+                for (int t = lo; t < hi; t++) A.out[ooff + t] = src[t];
             }
         }
     }
@@ -168,7 +149,8 @@ int run_apply_kernel(elp_ctx* c, bool with_lut) {
         A.seq = c->seq.p; A.qual = c->qual.p; A.out = c->qual_out.p; A.rg_cov = c->d_rg_cov; A.n_rg = c->n_rg; A.cov_exists = c->d_cov_exists;
         A.lut = with_lut ? c->d_lut : nullptr; A.lut_maxcyc = c->lut_maxcyc; A.max_cycle = c->max_cycle; A.err = c->d_err;
         const double bytes = (double)n * (2 + 4 + 4 + 8 + 8 + 8) + (double)c->n_seq + 2.0 * (double)c->n_qual;
-        const uint64_t reads_per_block = (uint64_t)WARPS * RPW;
+        A.lanes_per_read = std::min(32, std::max(1, (c->h_ranges.lseq_max + CHUNK - 1) / CHUNK));
+        const uint64_t reads_per_block = (uint64_t)WARPS * (32 / A.lanes_per_read);
         c->begin(with_lut ? "bqsr_apply" : "qual_materialize", bytes);
         bqsr_apply_kernel<<<(unsigned)((n + reads_per_block - 1) / reads_per_block), WARPS * 32, 0, c->stream>>>(A);
         c->end(); LAUNCH_CHECK(c);

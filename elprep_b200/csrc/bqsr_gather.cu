@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <vector>
 #include "ctx.h"
+#include "bqsr_simd.cuh"
 
 namespace {
 
@@ -178,7 +179,6 @@ struct __align__(16) ReadDesc {
 };                            // 48 bytes = three 16-byte loads: location | scalars | skip ranges
 constexpr uint8_t DF_REVERSED = 1, DF_LAST = 2, DF_SINGLE_M = 4, DF_SKIP_OVF = 8, DF_LEAN = 16;
 constexpr int OVF_WORDS = 16;   // 512 bits
-constexpr int CHUNK = 16;       // bases per lane in the chunk kernel
 
 struct GatherArgs {
     uint64_t n;
@@ -345,48 +345,6 @@ __device__ __forceinline__ void reds_inc(uint32_t a) { asm volatile("red.shared.
 // leaving ~14 instructions per base for the two shared-memory increments (cycle, context).  The cycle column of a
 // shared-memory row is skewed (cell c lives at c + c/16): the lanes of a read sit 16 cycles apart, which would otherwise
 // put them all on two banks.
-constexpr unsigned long long ONES = 0x1111111111111111ull;
-
-__device__ __forceinline__ void load16_unaligned(const uint8_t* p, uint32_t (&o)[4]) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint4* base = reinterpret_cast<const uint4*>(a & ~(uintptr_t)15);
-    const uint4 A0 = __ldg(base), A1 = __ldg(base + 1);
-    const uint32_t off = (uint32_t)a & 15u;
-    uint32_t w0 = A0.x, w1 = A0.y, w2 = A0.z, w3 = A0.w, w4 = A1.x, w5 = A1.y;
-    if (off & 8) { w0 = w2; w1 = w3; w2 = w4; w3 = w5; w4 = A1.z; w5 = A1.w; }
-    if (off & 4) { w0 = w1; w1 = w2; w2 = w3; w3 = w4; w4 = w5; }
-    const uint32_t sh = (off & 3) * 8;
-    o[0] = __funnelshift_r(w0, w1, sh); o[1] = __funnelshift_r(w1, w2, sh); o[2] = __funnelshift_r(w2, w3, sh); o[3] = __funnelshift_r(w3, w4, sh);
-}
-// 16 nibbles starting at nibble index `nidx` of a stream whose nibble 2b is the LOW nibble of byte b
-__device__ __forceinline__ unsigned long long load16_nibbles_le(const uint8_t* stream, uint64_t nidx) {
-    uint32_t o[4]; load16_unaligned(stream + (nidx >> 1), o);
-    const uint32_t sh = (uint32_t)(nidx & 1) * 4;
-    return (unsigned long long)__funnelshift_r(o[0], o[1], sh) | ((unsigned long long)__funnelshift_r(o[1], o[2], sh) << 32);
-}
-// the same for BAM SEQ (nibble 2b is the HIGH nibble of byte b)
-__device__ __forceinline__ unsigned long long load16_nibbles_bam(const uint8_t* stream, uint64_t nidx) {
-    uint32_t o[4]; load16_unaligned(stream + (nidx >> 1), o);
-#pragma unroll
-    for (int k = 0; k < 3; k++) o[k] = ((o[k] & 0x0f0f0f0fu) << 4) | ((o[k] >> 4) & 0x0f0f0f0fu);
-    const uint32_t sh = (uint32_t)(nidx & 1) * 4;
-    return (unsigned long long)__funnelshift_r(o[0], o[1], sh) | ((unsigned long long)__funnelshift_r(o[1], o[2], sh) << 32);
-}
-// 8 BAM nibbles -> 8 base codes (A=1 C=2 G=4 T=8 -> 0..3, anything else -> 8)
-__device__ __forceinline__ uint32_t codes_of(uint32_t v) {
-    const uint32_t code = (((v >> 1) & 0x77777777u) - ((v >> 3) & 0x11111111u)) & 0x33333333u;
-    uint32_t pc = v - ((v >> 1) & 0x55555555u); pc = (pc & 0x33333333u) + ((pc >> 2) & 0x33333333u);   // bits set per nibble
-    const uint32_t t = pc ^ 0x11111111u;                         // zero iff exactly one bit
-    const uint32_t bad = (t | (t >> 1) | (t >> 2)) & 0x11111111u;
-    return (code & ~(bad * 7u)) | (bad << 3);
-}
-// one flag per nibble for the bases lo..hi (clamped to the 16 of a chunk)
-__device__ __forceinline__ unsigned long long range_flags(int lo, int hi) {
-    lo = max(lo, 0); hi = min(hi, CHUNK - 1);
-    if (lo > hi) return 0ull;
-    return (ONES << (4 * lo)) & (ONES >> (4 * (CHUNK - 1 - hi)));
-}
-
 struct ChunkSmem { uint32_t obs, mis, qslot; };   // shared-window byte addresses
 
 __global__ void __launch_bounds__(256, 4) bqsr_chunk_kernel(GatherArgs A) {
@@ -435,19 +393,8 @@ __global__ void __launch_bounds__(256, 4) bqsr_chunk_kernel(GatherArgs A) {
         const unsigned long long inlen = range_flags(0, nb - 1);
         C = (C & (inlen * 15ull)) | ((ONES & ~inlen) << 3);                      // codes past the read end: 8
         // ---- low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2 ----
-        int first = 0x7fffffff, last = -1;
-        {
-            unsigned long long g01 = 0, g23 = 0;   // bit 7 of each byte: QUAL > 2
-#pragma unroll
-            for (int wq = 0; wq < 4; wq++) {
-                const uint32_t v = Q[wq], f = (((v & 0x7f7f7f7fu) + 0x7d7d7d7du) | v) & 0x80808080u;
-                if (wq < 2) g01 |= (unsigned long long)f << (32 * wq); else g23 |= (unsigned long long)f << (32 * (wq - 2));
-            }
-            // bytes past the read end are zero only if nb == 0; mask them
-            if (nb < 8) { g23 = 0; g01 &= nb > 0 ? (~0ull >> (8 * (8 - nb))) : 0ull; } else if (nb < 16) g23 &= (nb > 8) ? (~0ull >> (8 * (16 - nb))) : 0ull;
-            if (g01) first = i0 + ((__ffsll((long long)g01) - 1) >> 3); else if (g23) first = i0 + 8 + ((__ffsll((long long)g23) - 1) >> 3);
-            if (g23) last = i0 + 8 + ((63 - __clzll((long long)g23)) >> 3); else if (g01) last = i0 + ((63 - __clzll((long long)g01)) >> 3);
-        }
+        int first, last;
+        qual_gt2_span(Q, nb, i0, first, last);
         // the lanes of one read reduce among themselves (segmented by member mask)
         const unsigned gmask = lane_used ? ((lpr == 32 ? 0xffffffffu : ((1u << lpr) - 1u)) << (r * lpr)) : (1u << lane);
         const int leftPos = __reduce_min_sync(gmask, first), rightPos = __reduce_max_sync(gmask, last);
