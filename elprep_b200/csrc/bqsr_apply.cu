@@ -93,20 +93,42 @@ __global__ void __launch_bounds__(WARPS * 32) bqsr_apply_kernel(ApplyArgs A) {
         const unsigned long long okc = ~((Pn | C) >> 3) & ONES & range_flags(wlo - i0, whi - i0);
         const uint32_t ncyc17 = (2u * (uint32_t)A.lut_maxcyc + 1u) * 17u;
         const uint8_t* lut_cov = A.lut + (size_t)cov * 94u * ncyc17;
-        int cyc = cf + i0 * inc;
+        const uint32_t okc_w[2] = {(uint32_t)okc, (uint32_t)(okc >> 32)}, ctx_w[2] = {(uint32_t)ctxw, (uint32_t)(ctxw >> 32)};
+        const int cyc_a = cf + i0 * inc, cyc_b = cyc_a + (nb - 1) * inc;                    // cycles of the chunk's first / last base
+        // bytes past the read end must not look like bases (they belong to the next read of the arena and are never written back)
 #pragma unroll
-        for (int j = 0; j < CHUNK; j++) {
-            const uint32_t q = (Q[j >> 2] >> (8 * (j & 3))) & 0xffu;
-            if (j < nb && q >= 6) {                                                         // minInterestingQual
-                if (q > 93) errbits |= DERR_QUAL_RANGE;
-                else if (cyc > A.max_cycle || cyc < -A.max_cycle) errbits |= DERR_CYCLE;   // checkCycleCovariate :364-369
-                else {
-                    const uint32_t ctx = ((okc >> (4 * j)) & 1ull) ? (uint32_t)((ctxw >> (4 * j)) & 15ull) : 16u;   // 16 = no context (key -1)
-                    const uint32_t v = __ldg(lut_cov + q * ncyc17 + (uint32_t)(cyc + A.lut_maxcyc) * 17u + ctx);
-                    Q[j >> 2] = (Q[j >> 2] & ~(0xffu << (8 * (j & 3)))) | (v << (8 * (j & 3)));
-                }
+        for (int wq = 0; wq < 4; wq++) { const int keep = nb - 4 * wq; if (keep < 4) Q[wq] = keep <= 0 ? 0u : (Q[wq] & (0xffffffffu >> (8 * (4 - keep)))); }
+        if (max(cyc_a, cyc_b) > A.max_cycle || min(cyc_a, cyc_b) < -A.max_cycle) {
+            // checkCycleCovariate (:364-369) fails somewhere in this chunk: an error if one of those bases is recalibrated
+            int cyc = cyc_a;
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) {
+                const uint32_t q = (Q[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                if (q >= 6) errbits |= q > 93 ? DERR_QUAL_RANGE : ((cyc > A.max_cycle || cyc < -A.max_cycle) ? DERR_CYCLE : 0u);
+                cyc += inc;
             }
-            cyc += inc;
+        } else {
+            uint32_t idx = (uint32_t)(cyc_a + A.lut_maxcyc) * 17u;
+            const uint32_t step = (uint32_t)(inc * 17);
+            uint32_t over = 0;
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) {
+                const uint32_t q = (Q[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                const uint32_t nib = (ctx_w[j >> 3] >> (4 * (j & 7))) & 15u;
+                const uint32_t ctx = ((okc_w[j >> 3] >> (4 * (j & 7))) & 1u) ? nib : 16u;   // 16 = no context (key -1)
+                over |= q;
+                if (q - 6u <= 87u) {                                                        // minInterestingQual <= q <= 93
+                    const uint32_t v = __ldg(lut_cov + q * ncyc17 + idx + ctx);
+                    Q[j >> 2] = __byte_perm(Q[j >> 2], v, (j & 3) == 0 ? 0x3214 : ((j & 3) == 1 ? 0x3240 : ((j & 3) == 2 ? 0x3410 : 0x4210)));
+                }
+                idx += step;
+            }
+            // a QUAL above 93 (any byte with bit 7, or 94..127) is an error for a recalibrated base
+            if (over & 0x80u) errbits |= DERR_QUAL_RANGE;
+            else if (over >= 94u) {
+#pragma unroll
+                for (int wq = 0; wq < 4; wq++) { const uint32_t v = Q[wq]; if ((((v & 0x7f7f7f7fu) + 0x22222222u) | v) & 0x80808080u) errbits |= DERR_QUAL_RANGE; }
+            }
         }
     }
     *reinterpret_cast<uint4*>(&sm_o[w][lane * CHUNK]) = make_uint4(Q[0], Q[1], Q[2], Q[3]);

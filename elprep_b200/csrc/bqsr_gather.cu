@@ -332,7 +332,13 @@ __device__ __noinline__ void count_rare(const GatherArgs& A, int cov, int q, int
 
 // shared memory through explicit 32-bit shared-window addresses (generic pointers cost an address conversion per access)
 __device__ __forceinline__ int lds_s8(uint32_t a) { int v; asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void reds_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
+__device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// predicated form: no branch around the update
+__device__ __forceinline__ void reds_inc_if(uint32_t a, uint32_t p) {
+    asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %1, 0;\n\t@pp red.shared.add.u32 [%0], 1;\n\t}" ::"r"(a), "r"(p) : "memory");
+}
 
 // ---------------------------------------------------------------- kernel B: 16 consecutive bases per lane (the common case)
 // Reads whose clipped CIGAR is one M run (DF_LEAN, > 90 % of a WGS sample).  A warp takes 32 / lanes_per_read consecutive
@@ -349,13 +355,32 @@ struct ChunkSmem { uint32_t obs, mis, qslot; };   // shared-window byte addresse
 
 __global__ void __launch_bounds__(256, 4) bqsr_chunk_kernel(GatherArgs A) {
     extern __shared__ uint32_t sm_tab[];
-    __shared__ int8_t sm_qslot[256];      // QUAL -> shared-memory slot; -1: counted but no slot (or QUAL > 93); -2: QUAL < 6, not counted
+    // QUAL -> row of the CTA's tables: bits 0..5 = shared-memory slot, or n_slots = the trash row (updates that must not
+    // count land there, which keeps the per-base code free of predicates); bit 6: QUAL < 6 (never counted, bqsr.go:506);
+    // bit 7: counted but without a slot (or QUAL > 93) -> the chunk is redone base by base in the slow tail
+    __shared__ uint8_t sm_qslot[256];
+    __shared__ unsigned long long sm_ge[CHUNK + 1], sm_le[CHUNK + 1];   // nibble flags for index >= k / index <= k - 1
     const unsigned lane = lane_id();
-    const int cells = A.geom.n_cov * A.n_slots * A.ncols_s;
+    const int rows = A.n_slots + 1;
+    const int cells = A.geom.n_cov * rows * A.ncols_s;
     uint32_t* sm_mis = sm_tab + cells;
     for (int i = threadIdx.x; i < 2 * cells; i += blockDim.x) sm_tab[i] = 0;
-    { const int b = threadIdx.x; sm_qslot[b] = b < 6 ? (int8_t)-2 : (b < 94 ? A.qslot[b] : (int8_t)-1); }
+    {
+        const int b = threadIdx.x;
+        uint8_t v = (uint8_t)A.n_slots;
+        if (b < 6) v |= 0x40; else if (b < 94 && A.qslot[b] >= 0) v = (uint8_t)A.qslot[b]; else v |= 0x80;
+        sm_qslot[b] = v;
+        if (b <= CHUNK) { sm_ge[b] = b == CHUNK ? 0ull : (ONES << (4 * b)); sm_le[b] = b == 0 ? 0ull : (ONES >> (4 * (CHUNK - b))); }
+    }
     __syncthreads();
+    const uint32_t s_ge = (uint32_t)__cvta_generic_to_shared(sm_ge), s_le = (uint32_t)__cvta_generic_to_shared(sm_le);
+    // one flag per nibble for the bases lo..hi of a chunk (empty if lo > hi): two shared-memory look-ups
+    auto range16 = [&](int lo, int hi) -> unsigned long long {
+        unsigned long long ge, le;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(ge) : "r"(s_ge + 8u * (uint32_t)min(max(lo, 0), CHUNK)));
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(le) : "r"(s_le + 8u * (uint32_t)min(max(hi + 1, 0), CHUNK)));
+        return ge & le;
+    };
     ChunkSmem S;
     S.obs = (uint32_t)__cvta_generic_to_shared(sm_tab); S.mis = (uint32_t)__cvta_generic_to_shared(sm_mis); S.qslot = (uint32_t)__cvta_generic_to_shared(sm_qslot);
     const int Lc = A.Lc, lpr = A.lanes_per_read, rpw = 32 / lpr;
@@ -390,8 +415,7 @@ __global__ void __launch_bounds__(256, 4) bqsr_chunk_kernel(GatherArgs A) {
             R = load16_nibbles_le(A.refnib[refid], (uint64_t)((int64_t)(int32_t)sc.x - 1 + i0));
             C = (unsigned long long)codes_of((uint32_t)nibs) | ((unsigned long long)codes_of((uint32_t)(nibs >> 32)) << 32);
         }
-        const unsigned long long inlen = range_flags(0, nb - 1);
-        C = (C & (inlen * 15ull)) | ((ONES & ~inlen) << 3);                      // codes past the read end: 8
+        if (nb < CHUNK) { const unsigned long long inlen = range16(0, nb - 1); C = (C & (inlen * 15ull)) | ((ONES & ~inlen) << 3); }   // codes past the read end: 8
         // ---- low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2 ----
         int first, last;
         qual_gt2_span(Q, nb, i0, first, last);
@@ -414,10 +438,10 @@ __global__ void __launch_bounds__(256, 4) bqsr_chunk_kernel(GatherArgs A) {
             const uint4 sk = __ldg(dbase + 3 * kcur + 2);
             const uint32_t skv[4] = {sk.x, sk.y, sk.z, sk.w};
 #pragma unroll
-            for (int t = 0; t < 4; t++) if (t < (int)n_skip) skipf |= range_flags((int)(skv[t] & 0xffff) - i0, (int)(skv[t] >> 16) - i0);
+            for (int t = 0; t < 4; t++) if (t < (int)n_skip) skipf |= range16((int)(skv[t] & 0xffff) - i0, (int)(skv[t] >> 16) - i0);
         }
         const unsigned long long counted = ~(C >> 3) & ONES & ~skipf;                             // ACGT, inside the read, not a known site (QUAL >= 6 via the slot table)
-        const unsigned long long okc = counted & ~((Pn | C) >> 3) & range_flags(wlo - i0, whi - i0);
+        const unsigned long long okc = counted & ~((Pn | C) >> 3) & range16(wlo - i0, whi - i0);
         const unsigned long long X = C ^ R;
         const unsigned long long snpf = (X | (X >> 1) | (X >> 2) | (X >> 3)) & counted;         // computeSnpEvents, bqsr.go:254-285
         if (counted) {
@@ -426,34 +450,40 @@ __global__ void __launch_bounds__(256, 4) bqsr_chunk_kernel(GatherArgs A) {
         const int lastf = (flags & DF_LAST) ? 1 : 0;
         const int rof = 1 - 2 * lastf, inc = rev ? -rof : rof, cf = rof + (rev ? (L - 1) * rof : 0);   // prepareCycleCovariates, bqsr.go:376-383
         const int ci0 = cf + i0 * inc + Lc;                                                          // cycle cell of the chunk's first base
-        const uint32_t obs0 = S.obs + cov * (uint32_t)A.n_slots * row_bytes;
-        unsigned long long later = snpf;                                                             // bases needing the slow tail: mismatches and slot-less QUAL
+        const uint32_t obs0 = S.obs + cov * (uint32_t)rows * row_bytes;
+        const uint32_t cnt_w[2] = {(uint32_t)counted, (uint32_t)(counted >> 32)}, okc_w[2] = {(uint32_t)okc, (uint32_t)(okc >> 32)};
+        const uint32_t ctx_w[2] = {(uint32_t)ctxw, (uint32_t)(ctxw >> 32)};
+        const uint32_t obs_ctx = obs0 + ctx_off;
+        uint32_t racc = 0;
         int ci = ci0;
 #pragma unroll
         for (int j = 0; j < CHUNK; j++) {
+            // no predicates and no branches: a base that is not counted adds 0, a QUAL without a slot adds to the trash row
             const uint32_t q = (Q[j >> 2] >> (8 * (j & 3))) & 0xffu;
-            const int slot = lds_s8(S.qslot + q);
-            const bool cnt = (counted >> (4 * j)) & 1ull;
-            if (cnt && slot >= 0) {
-                const uint32_t orow = obs0 + (uint32_t)slot * row_bytes;
-                reds_inc(orow + (uint32_t)(ci + (ci >> 4)) * 4u);
-                if ((okc >> (4 * j)) & 1ull) reds_inc(orow + ctx_off + (uint32_t)((ctxw >> (4 * j)) & 15ull) * 4u);
-            }
-            if (cnt && slot == -1) later |= 1ull << (4 * j);
-            if (slot == -2) later &= ~(1ull << (4 * j));                                           // QUAL < 6: not counted at all
+            const uint32_t lut = lds_u8(S.qslot + q);
+            const uint32_t roff = (lut & 0x3fu) * row_bytes;
+            const uint32_t a1 = obs0 + roff + (uint32_t)(ci + (ci >> 4)) * 4u;
+            const uint32_t nib4 = (j & 7) == 0 ? ((ctx_w[j >> 3] << 2) & 0x3cu) : ((ctx_w[j >> 3] >> (4 * (j & 7) - 2)) & 0x3cu);
+            const uint32_t a2 = obs_ctx + roff + nib4;
+            reds_add(a1, (cnt_w[j >> 3] >> (4 * (j & 7))) & 1u);
+            reds_add(a2, (okc_w[j >> 3] >> (4 * (j & 7))) & 1u);
+            racc |= lut;
             ci += inc;
         }
+        // slow tail: mismatches (sparse) and, if some base of the chunk has a QUAL without a shared-memory slot, all counted bases
+        unsigned long long later = (racc & 0x80u) ? counted : snpf;
         while (later) {
             const int j = (__ffsll((long long)later) - 1) >> 2;
             later &= ~(15ull << (4 * j));
             const uint32_t qw = j < 4 ? Q[0] : (j < 8 ? Q[1] : (j < 12 ? Q[2] : Q[3]));
             const uint32_t q = (qw >> (8 * (j & 3))) & 0xffu;
-            const int slot = lds_s8(S.qslot + q);
+            const uint32_t lut = lds_u8(S.qslot + q);
             const int cj = ci0 + j * inc;
             const uint32_t ctx = (uint32_t)((ctxw >> (4 * j)) & 15ull);
             const bool ok = (okc >> (4 * j)) & 1ull, snp = (snpf >> (4 * j)) & 1ull;
-            if (slot >= 0) {          // a mismatch (sparse, ~0.5 % of bases) on the CTA's second table
-                const uint32_t mrow = S.mis + (cov * (uint32_t)A.n_slots + (uint32_t)slot) * row_bytes;
+            if ((lut & 0x40u) || (!(lut & 0x80u) && !snp)) continue;   // QUAL < 6: not counted; slotted match: done in the fast loop
+            if (!(lut & 0x80u)) {     // a mismatch (sparse, ~0.5 % of bases) on the CTA's second table
+                const uint32_t mrow = S.mis + (cov * (uint32_t)rows + (lut & 0x3fu)) * row_bytes;
                 reds_inc(mrow + (uint32_t)(cj + (cj >> 4)) * 4u);
                 if (ok) reds_inc(mrow + ctx_off + ctx * 4u);
             } else count_rare(A, (int)cov, (int)q, cj - Lc, ctx, ok, snp ? 1u : 0u, false, &errbits);
@@ -468,7 +498,8 @@ __global__ void __launch_bounds__(256, 4) bqsr_chunk_kernel(GatherArgs A) {
     for (int i = threadIdx.x; i < cells; i += blockDim.x) {
         const uint32_t v = sm_tab[i], e = sm_mis[i];
         if (!(v | e)) continue;
-        const int col_s = i % ncols_s, cs = i / ncols_s, slot = cs % A.n_slots, cov = cs / A.n_slots;
+        const int col_s = i % ncols_s, cs = i / ncols_s, slot = cs % rows, cov = cs / rows;
+        if (slot == A.n_slots) continue;   // trash row
         int col_g;
         if (col_s < ctx_col) { const int cyc_cell = 16 * (col_s / 17) + col_s % 17; col_g = A.geom.col_cycle(cyc_cell - Lc); }   // undo the skew
         else col_g = A.geom.col_ctx(col_s - ctx_col);
@@ -728,11 +759,11 @@ int phase_bqsr_gather(elp_ctx* c) {
             for (int q = 6; q < 94; q++) if (h[q]) qs.push_back(q);
             std::sort(qs.begin(), qs.end(), [&](int a, int b) { return h[a] != h[b] ? h[a] > h[b] : a < b; });
             const size_t per_slot = (size_t)std::max(1, c->geom.n_cov) * A.ncols_s * 4;
-            const int max_slots = (int)std::min<size_t>(94, (48 * 1024) / (2 * per_slot));   // observation + mismatch tables
-            A.n_slots = std::min<int>((int)qs.size(), max_slots);
+            const int max_slots = (int)std::min<size_t>(63, (48 * 1024) / (2 * per_slot)) - 1;   // observation + mismatch tables, one trash row each
+            A.n_slots = std::max(0, std::min<int>((int)qs.size(), max_slots));
             for (int s = 0; s < A.n_slots; s++) { A.qslot[qs[s]] = (int8_t)s; A.slot_q[s] = (uint8_t)qs[s]; }
         }
-        const size_t smem = (size_t)c->geom.n_cov * A.n_slots * A.ncols_s * 4 * 2;
+        const size_t smem = (size_t)c->geom.n_cov * (A.n_slots + 1) * A.ncols_s * 4 * 2;
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         // descriptors (32 B/read) and the overflow skip bitmasks live in scratch buffers that are free in this phase
         CUDA_TRY(c, c->keys_a.reserve(n * 6 + 8, c->stream));

@@ -8,17 +8,17 @@ import numpy as np
 from elprep_b200 import synth, device
 import bench
 contigs = synth.scaled_hg38(20.0)
-w = synth.make_workload(5_000_000, contigs, seed=20260924, threads=32)
+w = synth.make_workload(15_000_000, contigs, seed=20260924, threads=32)
 hb = bench.pinned(w.batch)
 ctx = device.Context(w.header, profile=True)
 for ci in range(len(contigs)):
     ctx.set_reference(ci, w.contig_bases[ci]); ctx.set_known_sites(ci, w.sites[ci], True)
 for rep in range(3):
-    ctx.reset(); ctx.append(hb); ctx.sort_markdup(); ctx.reset_stats(); ctx.bqsr_gather(); ctx.synchronize()
+    ctx.reset(); ctx.append(hb); ctx.sort_markdup(); ctx.reset_stats(); ctx.bqsr_gather(); ctx.bqsr_finalize(None); ctx.bqsr_apply(); ctx.synchronize()
 st = ctx.kernel_stats()
-print(os.environ.get("ELPREP_B200_LIB","default").split("/")[-1], "gather %%.2f ms  prep %%.2f ms" %% (st["bqsr_gather"]["ms"], st["bqsr_prep"]["ms"]), flush=True)
+print(os.environ.get("ELPREP_B200_LIB","default").split("/")[-1], "  ".join("%%s %%.2f" %% (k, st[k]["ms"]) for k in ("bqsr_gather", "bqsr_gather_general", "bqsr_prep", "bqsr_apply") if k in st), flush=True)
 ''' % ROOT
 for name in sys.argv[1:]:
     env = dict(os.environ)
-    env["ELPREP_B200_LIB"] = os.path.join(ROOT, "elprep_b200", "lib", "exp", f"lib_{name}.so")
+    env["ELPREP_B200_LIB"] = os.path.join(ROOT, "elprep_b200", "lib", "libelprep_b200.so" if name == "default" else os.path.join("exp", f"lib_{name}.so"))
     subprocess.run([sys.executable, "-c", child], env=env)
