@@ -21,6 +21,10 @@ namespace {
 
 constexpr int WARPS = 8;
 
+// nibble flags for chunk index >= k and <= k - 1 (filled by run_apply_kernel)
+__constant__ unsigned long long c_ge[CHUNK + 1], c_le[CHUNK + 1];
+__device__ __forceinline__ unsigned long long range16(int lo, int hi) { return c_ge[min(max(lo, 0), CHUNK)] & c_le[min(max(hi + 1, 0), CHUNK)]; }
+
 struct ApplyArgs {
     uint64_t n;
     const uint16_t* flag; const int32_t *rg, *lseq; const uint64_t *qual_off, *seq_off, *out_off;
@@ -31,17 +35,13 @@ struct ApplyArgs {
     uint32_t* err;
 };
 
-__device__ __forceinline__ uint32_t lds_unaligned32(const uint8_t* p) {   // 4 bytes at any shared-memory address
-    const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
-    const uint32_t base = a & ~3u, sh = (a & 3u) * 8u;
-    uint32_t lo, hi;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(base));
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"(base + 4));
-    return __funnelshift_r(lo, hi, sh);
-}
-
-__global__ void __launch_bounds__(WARPS * 32) bqsr_apply_kernel(ApplyArgs A) {
-    __shared__ __align__(16) uint8_t sm_o[WARPS][32 * CHUNK + 16];   // one 16-byte cell per lane; the cells of a read are contiguous
+#ifndef APPLY_MINB
+#define APPLY_MINB 8
+#endif
+__global__ void __launch_bounds__(WARPS * 32, APPLY_MINB) bqsr_apply_kernel(ApplyArgs A) {
+    // image of the block's slice of the output stream, placed with the slice's 16-byte phase: the reads of a block are
+    // consecutive in output order, so the whole slice leaves as aligned 128-bit stores (two partial chunks per BLOCK)
+    __shared__ __align__(16) uint8_t sm_img[WARPS * 32 * CHUNK + 32];
     const unsigned lane = lane_id(), w = threadIdx.x >> 5;
     const int lpr = A.lanes_per_read, rpw = 32 / lpr;
     const int r = (int)lane / lpr, c = (int)lane - r * lpr;
@@ -52,6 +52,9 @@ __global__ void __launch_bounds__(WARPS * 32) bqsr_apply_kernel(ApplyArgs A) {
     uint32_t errbits = 0;
     if (L > CHUNK * lpr) { errbits |= DERR_READLEN_LIMIT; L = 0; }
     const uint64_t qoff = valid ? A.qual_off[k] : 0, ooff = valid ? A.out_off[k] : 0;
+    const uint64_t kb0 = (uint64_t)blockIdx.x * WARPS * (uint64_t)rpw, kb1 = min(A.n, kb0 + (uint64_t)(WARPS * rpw));
+    const uint64_t o0 = A.out_off[kb0], o1 = A.out_off[kb1];               // the block's slice [o0, o1) of the output stream
+    const uint32_t phase = (uint32_t)(o0 & 15);
     bool recal = valid && A.lut != nullptr && L > 0;
     int cov = 0;
     if (recal) {
@@ -65,13 +68,12 @@ __global__ void __launch_bounds__(WARPS * 32) bqsr_apply_kernel(ApplyArgs A) {
     unsigned long long C = 0;
     if (nb > 0) {
         load16_unaligned(A.qual + qoff + (uint64_t)i0, Q);
-        if (recal) {
+        if (A.lut != nullptr) {   // (not `recal`: the read-group look-ups above overlap with these loads)
             const unsigned long long nibs = load16_nibbles_bam(A.seq, A.seq_off[k] * 2 + (uint64_t)i0);
             C = (unsigned long long)codes_of((uint32_t)nibs) | ((unsigned long long)codes_of((uint32_t)(nibs >> 32)) << 32);
         }
     }
-    const unsigned long long inlen = range_flags(0, nb - 1);
-    C = (C & (inlen * 15ull)) | ((ONES & ~inlen) << 3);                          // codes past the read end: 8
+    if (nb < CHUNK) { const unsigned long long inlen = range16(0, nb - 1); C = (C & (inlen * 15ull)) | ((ONES & ~inlen) << 3); }   // codes past the read end: 8
     int first, last;
     qual_gt2_span(Q, nb, i0, first, last);
     const unsigned gmask = lane_used ? ((lpr == 32 ? 0xffffffffu : ((1u << lpr) - 1u)) << (r * lpr)) : (1u << lane);
@@ -90,7 +92,7 @@ __global__ void __launch_bounds__(WARPS * 32) bqsr_apply_kernel(ApplyArgs A) {
         const unsigned long long M3 = 0x3333333333333333ull, xr = rev ? M3 : 0ull;
         const unsigned long long ctxw = ((Pn ^ xr) & M3) | (((C ^ xr) & M3) << 2);          // key>>4 = prev | cur<<2, complemented for reverse reads
         const int wlo = rev ? leftPos : leftPos + 1, whi = rev ? rightPos - 1 : rightPos;      // low-quality tails read as N
-        const unsigned long long okc = ~((Pn | C) >> 3) & ONES & range_flags(wlo - i0, whi - i0);
+        const unsigned long long okc = ~((Pn | C) >> 3) & ONES & range16(wlo - i0, whi - i0);
         const uint32_t ncyc17 = (2u * (uint32_t)A.lut_maxcyc + 1u) * 17u;
         const uint8_t* lut_cov = A.lut + (size_t)cov * 94u * ncyc17;
         const uint32_t okc_w[2] = {(uint32_t)okc, (uint32_t)(okc >> 32)}, ctx_w[2] = {(uint32_t)ctxw, (uint32_t)(ctxw >> 32)};
@@ -131,24 +133,20 @@ __global__ void __launch_bounds__(WARPS * 32) bqsr_apply_kernel(ApplyArgs A) {
             }
         }
     }
-    *reinterpret_cast<uint4*>(&sm_o[w][lane * CHUNK]) = make_uint4(Q[0], Q[1], Q[2], Q[3]);
-    __syncwarp();
-    // ---- 3. write the strip in 16-byte chunks aligned on the output stream ----
-    if (L > 0) {
-        const uint32_t osh = (uint32_t)(ooff & 15);
-        const uint64_t oa = ooff & ~15ull;
-        const int noc = (int)((osh + (uint32_t)L + 15u) >> 4);
-        const uint8_t* src = &sm_o[w][r * lpr * CHUNK];
-        for (int cc = c; cc < noc; cc += lpr) {
-            const int r0 = 16 * cc - (int)osh;                                              // read coordinate of the chunk's first byte
-            if (r0 >= 0 && r0 + 16 <= L) {
-                uint4 v;
-                v.x = lds_unaligned32(src + r0); v.y = lds_unaligned32(src + r0 + 4); v.z = lds_unaligned32(src + r0 + 8); v.w = lds_unaligned32(src + r0 + 12);
-                *reinterpret_cast<uint4*>(A.out + oa + 16ull * cc) = v;
-            } else {
-                const int lo = max(r0, 0), hi = min(r0 + 16, L);                            // partial chunk shared with the neighbouring read
-                for (int t = lo; t < hi; t++) A.out[ooff + t] = src[t];
-            }
+    // ---- 3. park the chunk in the block image, then write the image in 16-byte chunks aligned on the output stream ----
+    if (nb > 0) {
+        uint8_t* dst = sm_img + phase + (uint32_t)(ooff - o0) + (uint32_t)i0;
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) if (j < nb) dst[j] = (uint8_t)(Q[j >> 2] >> (8 * (j & 3)));
+    }
+    __syncthreads();
+    {
+        const uint32_t total = (uint32_t)(o1 - o0), end = phase + total;           // image bytes [phase, end)
+        uint8_t* gbase = A.out + (o0 - phase);                                      // 16-byte aligned
+        for (uint32_t m = threadIdx.x; m * 16u < end; m += blockDim.x) {
+            const uint32_t b0 = m * 16u;
+            if (b0 >= phase && b0 + 16u <= end) *reinterpret_cast<uint4*>(gbase + b0) = *reinterpret_cast<const uint4*>(sm_img + b0);
+            else { const uint32_t lo = max(b0, phase), hi = min(b0 + 16u, end); for (uint32_t t = lo; t < hi; t++) gbase[t] = sm_img[t]; }   // shared with a neighbouring block
         }
     }
     for (int o = 16; o; o >>= 1) errbits |= __shfl_xor_sync(FULL_MASK, errbits, o);
@@ -166,6 +164,13 @@ int run_apply_kernel(elp_ctx* c, bool with_lut) {
     }
     CUDA_TRY(c, c->qual_out.reserve(total + 64, c->stream));
     if (n) {
+        static bool tables_set[64] = {false};
+        if (!tables_set[c->device & 63]) {
+            unsigned long long ge[CHUNK + 1], le[CHUNK + 1];
+            for (int b = 0; b <= CHUNK; b++) { ge[b] = b == CHUNK ? 0ull : (ONES << (4 * b)); le[b] = b == 0 ? 0ull : (ONES >> (4 * (CHUNK - b))); }
+            CUDA_TRY(c, cudaMemcpyToSymbol(c_ge, ge, sizeof ge)); CUDA_TRY(c, cudaMemcpyToSymbol(c_le, le, sizeof le));
+            tables_set[c->device & 63] = true;
+        }
         ApplyArgs A{};
         A.n = n; A.flag = c->s_flag.p; A.rg = c->s_rg.p; A.lseq = c->s_lseq.p; A.qual_off = c->s_qual_off.p; A.seq_off = c->s_seq_off.p; A.out_off = c->s_out_off.p;
         A.seq = c->seq.p; A.qual = c->qual.p; A.out = c->qual_out.p; A.rg_cov = c->d_rg_cov; A.n_rg = c->n_rg; A.cov_exists = c->d_cov_exists;

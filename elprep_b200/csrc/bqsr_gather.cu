@@ -353,7 +353,10 @@ __device__ __forceinline__ void reds_inc_if(uint32_t a, uint32_t p) {
 // put them all on two banks.
 struct ChunkSmem { uint32_t obs, mis, qslot; };   // shared-window byte addresses
 
-__global__ void __launch_bounds__(256, 4) bqsr_chunk_kernel(GatherArgs A) {
+#ifndef CHUNK_MINB
+#define CHUNK_MINB 4
+#endif
+__global__ void __launch_bounds__(256, CHUNK_MINB) bqsr_chunk_kernel(GatherArgs A) {
     extern __shared__ uint32_t sm_tab[];
     // QUAL -> row of the CTA's tables: bits 0..5 = shared-memory slot, or n_slots = the trash row (updates that must not
     // count land there, which keeps the per-base code free of predicates); bit 6: QUAL < 6 (never counted, bqsr.go:506);
@@ -783,7 +786,7 @@ int phase_bqsr_gather(elp_ctx* c) {
         gen_list_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(A);
         c->end(); LAUNCH_CHECK(c);
         const uint64_t rpw = 32 / A.lanes_per_read, steps = (n + rpw - 1) / rpw;
-        uint64_t grid = std::min<uint64_t>((steps + 7) / 8, (uint64_t)sms * 4);
+        uint64_t grid = std::min<uint64_t>((steps + 7) / 8, (uint64_t)sms * CHUNK_MINB);
         grid = std::max<uint64_t>(grid, (n + (4u << 20) - 1) / (4u << 20));   // <= 4 M reads per CTA keeps the 32-bit shared counters far from overflow
         CUDA_TRY(c, cudaFuncSetAttribute(bqsr_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
         c->begin("bqsr_gather", bytes);
