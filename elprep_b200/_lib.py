@@ -30,7 +30,7 @@ class ElpDupMetrics(C.Structure):
     COUNTERS = ("unpaired_reads_examined", "read_pairs_examined", "secondary_or_supplementary_reads", "unmapped_reads",
                 "unpaired_read_duplicates", "read_pair_duplicates", "read_pair_optical_duplicates")
     _fields_ = [(k, C.c_int64) for k in COUNTERS] + [("estimated_library_size", C.c_int64), ("percent_duplication", C.c_double),
-                                                      ("roi", C.c_double * 100), ("has_roi", C.c_int32)]
+                                                      ("roi", C.c_double * 100), ("has_roi", C.c_int32), ("paired_reads_examined", C.c_int64)]
 
 
 class ElpKernelStat(C.Structure):

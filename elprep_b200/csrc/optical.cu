@@ -341,7 +341,6 @@ int phase_optical(elp_ctx* c, uint64_t npairs, const uint64_t* sorted_keys, cons
     for (size_t s = 0; s < slots; s++) {
         DupCounters& d = c->opt[s];
         for (int k = 0; k < 7; k++) d.ctr[k] = (int64_t)h_ctr[s * OPT_NCTR + k];
-        d.ctr[1] /= 2;                                                   // ReadPairsExamined counts reads (:503-505)
         for (int w = 0; w < 3; w++)
             for (int k = 0; k < OPT_HBINS; k++) { const unsigned long long v = h_hist[(s * 3 + w) * OPT_HBINS + k]; if (v) d.hist[w][k] += (int64_t)v; }
     }
@@ -370,7 +369,11 @@ static int64_t estimate_library_size(int64_t n_pairs, int64_t n_unique) {
 }
 
 // calculateDerivedDuplicateMetrics (:519-525), estimateRoi (:570-572), histogramRoi (:574-581)
-static void derive(const DupCounters& d, elp_dup_metrics* m) {
+// DupCounters.ctr[1] counts paired READS (the reference halves after its reduction, :503-505; keeping reads makes the sum
+// over several workers exact); everything derived uses pairs.
+static void derive(const DupCounters& d0, elp_dup_metrics* m) {
+    DupCounters d = d0; d.ctr[1] = d0.ctr[1] / 2;
+    m->paired_reads_examined = d0.ctr[1];
     m->unpaired_reads_examined = d.ctr[0]; m->read_pairs_examined = d.ctr[1]; m->secondary_or_supplementary_reads = d.ctr[2]; m->unmapped_reads = d.ctr[3];
     m->unpaired_read_duplicates = d.ctr[4]; m->read_pair_duplicates = d.ctr[5]; m->read_pair_optical_duplicates = d.ctr[6];
     m->estimated_library_size = 0; m->has_roi = 0;

@@ -113,6 +113,7 @@ class Context:
             d["estimated_library_size"] = int(m.estimated_library_size)
             d["percent_duplication"] = float(m.percent_duplication)
             d["roi"] = list(m.roi) if m.has_roi else None
+            d["paired_reads_examined"] = int(m.paired_reads_examined)
             hs = []
             for which in range(3):
                 n = int(self.L.elp_optical_histogram(self.h, slot, which, None, None, 0))
@@ -126,7 +127,8 @@ class Context:
         return out
 
     def optical_merge(self, slot, counters=None, hist=None):
-        """add another worker's numbers (mergeDuplicatesCtrMaps): counters = 7 ints in DuplicatesCtr order, hist = 3 dicts"""
+        """add another worker's numbers (mergeDuplicatesCtrMaps): counters = 7 ints in DuplicatesCtr order except that
+        counters[1] counts paired READS (that worker's paired_reads_examined); hist = 3 dicts"""
         c7 = np.ascontiguousarray(counters, dtype=np.int64) if counters is not None else None
         if c7 is not None:
             self._ck(self.L.elp_optical_merge(self.h, slot, _vp(c7), 0, None, None, 0))

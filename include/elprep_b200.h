@@ -125,6 +125,7 @@ typedef struct {
     int64_t estimated_library_size;       /* estimateLibrarySize (:533-562); 0 unless read_pairs_examined > 0 */
     double percent_duplication;           /* NaN when nothing was examined, as in the reference (:524) */
     double roi[100]; int32_t has_roi;     /* histogramRoi (:574-581) */
+    int64_t paired_reads_examined;        /* reads behind read_pairs_examined (= 2x + an unmatched mate, :488,503-505) */
 } elp_dup_metrics;
 int32_t elp_optical_n_libraries(const elp_ctx *ctx);                    /* number of slots */
 const char *elp_optical_library_name(const elp_ctx *ctx, int32_t slot);
@@ -132,8 +133,9 @@ int elp_optical_metrics(elp_ctx *ctx, int32_t slot, elp_dup_metrics *out);
 /* which: 0 duplicatesCountHistogram, 1 nonOpticalDuplicatesCountHistogram, 2 opticalDuplicatesCountHistogram;
  * writes up to cap (key, count) pairs in ascending key order, returns the number of entries (-1 on error) */
 int64_t elp_optical_histogram(elp_ctx *ctx, int32_t slot, int32_t which, int64_t *keys, int64_t *counts, int64_t cap);
-/* mergeDuplicatesCtrMaps / LoadAndCombineDuplicateMetrics (:451-466, :711-731): add another worker's counters (7 values,
- * may be NULL) and/or one of its histograms; derived metrics are recomputed on the next read-out */
+/* mergeDuplicatesCtrMaps / LoadAndCombineDuplicateMetrics (:451-466, :711-731): add another worker's counters (7 values in
+ * the order of elp_dup_metrics, but counters7[1] = that worker's paired_reads_examined so that the halving happens once,
+ * after the sum; may be NULL) and/or one of its histograms; derived metrics are recomputed on the next read-out */
 int elp_optical_merge(elp_ctx *ctx, int32_t slot, const int64_t *counters7, int32_t which, const int64_t *keys, const int64_t *counts, int64_t n);
 /* PrintDuplicatesMetrics (:601-699). The reference prints libraries in Go map order; here ascending by name.
  * started_on replaces time.Now().Format(...) so that the output is reproducible. */

@@ -40,3 +40,36 @@ def test_product_does_not_import_oracle():
                 if re.search(r"^\s*(import|from)\s+oracle\b", s, re.M) or "liboracle" in s or "oracle/" in s.replace("the oracle/", ""):
                     bad.append(f)
     assert not bad, bad
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "cabi_client")
+    libdir = os.path.join(ROOT, "elprep_b200", "lib")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "cabi_client.c"),
+                           "-o", exe, "-L", libdir, "-lelprep_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_c_client_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """the header is valid C99 and a plain C program links against the library; without a GPU elp_create returns ELP_ENODEVICE"""
+    import subprocess
+    import torch
+    exe = _build_c_client(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    if not torch.cuda.is_available():
+        assert out.stdout.startswith("nodevice:") and "no CPU fallback" in out.stdout
+
+
+@pytest.mark.gpu
+def test_c_client_runs_the_path(tmp_path):
+    import subprocess
+    exe = _build_c_client(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().split("\n")
+    # coordinate order: POS 20 (read 2), the two reads at POS 50 by QNAME (r1 < r2), the unmapped read last; r2 (score 80 < 120) is the duplicate
+    assert lines[0] == "order 2 0 1 3 flags 16 0 1024 4", out.stdout
+    assert lines[1] == "libA unpaired 3 dups 1 unmapped 1"
+    assert lines[2] == "apply-before-finalize rc -16"

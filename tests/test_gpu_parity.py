@@ -302,3 +302,64 @@ def test_optical_hand_cases():
     with pytest.raises(device.ElprepError):
         ctx.optical_metrics()
     ctx.close()
+
+
+def test_two_workers_spread_pairs_on_device():
+    """two contig-group workers in one process (threads stand in for ranks): cross-group pairs are exchanged
+    (elprep_b200.multi), duplicate flags and the merged duplication metrics equal the whole-file run of the oracle"""
+    import threading
+    import oracle
+    from elprep_b200 import device, multi, _lib
+    contigs = [("c1", 300_000), ("c2", 250_000), ("c3", 120_000), ("c4", 80_000)]
+    w = synth.make_workload(6000, contigs, seed=92, cross_contig_frac=0.3, dup_frac=0.4, optical_frac=0.3, want_reference=False)
+    whole = w.batch.copy()
+    wm = oracle.markdup_optical(whole, w.header)
+    world = 2
+    groups = multi.contig_groups(contigs, world)
+    owner = multi.owner_table(w.header, groups)
+    slots, bar, out, errs = [None] * world, threading.Barrier(world), [None] * world, []
+
+    def gather_for(rank):
+        def gather(obj):
+            slots[rank] = obj
+            bar.wait()
+            res = list(slots)
+            bar.wait()
+            return res
+        return gather
+
+    def worker(rank):
+        try:
+            own = multi.partition(w.batch, owner, rank, world)
+            sub = w.batch.take(own)
+            sm = multi.exchange_spread_duplicates(sub, w.header, owner, rank, world, multi.device_markdup(0, optical=True), gather_for(rank))
+            ctx = device.Context(w.header)
+            ctx.append(sub)
+            ctx.sort_markdup(device.SO_COORDINATE, _lib.MARKDUP_OPTICAL)
+            multi.merge_spread_metrics(ctx, sm)
+            idx, flag, _, _ = ctx.fetch(want_qual=False)
+            fl = np.empty(sub.n, np.uint16); fl[idx.astype(np.int64)] = flag
+            out[rank] = (own, fl, ctx.optical_metrics())
+            ctx.close()
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+            bar.abort()
+
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert not errs, errs
+    for own, fl, _ in out:
+        assert np.array_equal(fl, whole.flag[own])
+    # sum of the workers' metrics (mergeDuplicatesCtrMaps) == whole-file metrics
+    ctx = device.Context(w.header)
+    for slot in range(len(wm.counters)):
+        for _, _, m in out:
+            c7 = [m[slot][k] for k in _lib.ElpDupMetrics.COUNTERS]
+            c7[1] = m[slot]["paired_reads_examined"]
+            ctx.optical_merge(slot, c7, m[slot]["hist"])
+    tot = ctx.optical_metrics()
+    for slot, g in enumerate(tot):
+        assert [g[k] for k in _lib.ElpDupMetrics.COUNTERS] == [wm.counters[slot][k] for k in oracle.COUNTERS], slot
+        assert g["hist"] == wm.hist[slot] and g["estimated_library_size"] == wm.library_size[slot]
+    ctx.close()

@@ -76,3 +76,81 @@ def test_two_rank_partition_equals_whole(tmp_path):
         pos_in_whole = {int(v): k for k, v in enumerate(perm)}
         ranks = [pos_in_whole[int(i)] for i in idx]
         assert ranks == sorted(ranks)
+
+
+# ---- cross-group mate pairs: the reference's "spread" reads (sam/split-merge.go:286-293) as an exchange between the ranks ----
+SPREAD_CONTIGS = [("c1", 300_000), ("c2", 250_000), ("c3", 120_000), ("c4", 80_000)]
+SPREAD_KW = dict(seed=91, cross_contig_frac=0.3, dup_frac=0.4, optical_frac=0.3, want_reference=False, threads=2)
+
+
+def _spread_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import pickle
+    import torch.distributed as dist
+    import oracle
+    from elprep_b200 import synth, multi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    w = synth.make_workload(5000, SPREAD_CONTIGS, **SPREAD_KW)
+    groups = multi.contig_groups(SPREAD_CONTIGS, world)
+    owner = multi.owner_table(w.header, groups)
+    own = multi.partition(w.batch, owner, rank, world)
+    sub = w.batch.take(own)
+
+    def orc_markdup(batch, header):                    # same contract as multi.device_markdup, on the CPU restatement
+        b = batch.copy()
+        m = oracle.markdup_optical(b, header)
+        return b.flag, m
+
+    n_spread = multi.spread_reads(sub, owner, rank)[0].size
+    sm = multi.exchange_spread_duplicates(sub, w.header, owner, rank, world, orc_markdup, multi.torch_gather_objects())
+    mm = oracle.markdup_optical(sub, w.header)         # the rank's main pass (spread reads arrive with their 0x400 bit preset)
+    with open(os.path.join(out_dir, f"spread_{rank}.pkl"), "wb") as f:
+        pickle.dump(dict(own=own, flag=sub.flag.copy(), n_spread=n_spread, main=(mm.counters, mm.hist), spread=(sm.counters, sm.hist) if sm else None), f)
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_two_rank_spread_pairs(tmp_path):
+    import pickle
+    import torch.multiprocessing as mp
+    sys.path.insert(0, ROOT)
+    import oracle
+    from elprep_b200 import synth
+    port = 29900 + (os.getpid() % 90)
+    mp.spawn(_spread_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    w = synth.make_workload(5000, SPREAD_CONTIGS, **SPREAD_KW)
+    whole = w.batch.copy()
+    wm = oracle.markdup_optical(whole, w.header)
+    res = [pickle.load(open(os.path.join(tmp_path, f"spread_{r}.pkl"), "rb")) for r in range(2)]
+    assert sum(r["n_spread"] for r in res) > 200
+    seen = np.zeros(whole.n, bool)
+    spread_dups = 0
+    for r in res:
+        assert np.array_equal(r["flag"], whole.flag[r["own"]]), "FLAG of a partitioned run differs from the whole-file run"
+        seen[r["own"]] = True
+    assert seen.all()
+    # duplication metrics: per-read counters from the main passes, pair-level numbers from main + spread passes
+    n_slots = len(wm.counters)
+    for slot in range(n_slots):
+        tot = {k: 0 for k in oracle.COUNTERS}
+        hist = [dict(), dict(), dict()]
+        for r in res:
+            for k in oracle.COUNTERS:
+                tot[k] += r["main"][0][slot][k]
+            parts = [r["main"][1][slot]] + ([r["spread"][1][slot]] if r["spread"] else [])
+            if r["spread"]:
+                for k in ("read_pair_duplicates", "read_pair_optical_duplicates"):
+                    tot[k] += r["spread"][0][slot][k]
+                spread_dups += r["spread"][0][slot]["read_pair_duplicates"]
+            for p in parts:
+                for wh in range(3):
+                    for key, v in p[wh].items():
+                        hist[wh][key] = hist[wh].get(key, 0) + v
+        exp = wm.counters[slot]
+        for k in oracle.COUNTERS:
+            if k == "read_pairs_examined":          # halved per worker (:503-505): off by at most one per worker
+                assert 0 <= exp[k] - tot[k] <= 2
+            else:
+                assert tot[k] == exp[k], (slot, k)
+        assert hist == wm.hist[slot], slot
+    assert spread_dups > 10
