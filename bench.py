@@ -90,12 +90,8 @@ def pinned(batch):
 
 
 def contig_groups(contigs, n):
-    """sfm-style contig groups (sam/split-merge.go:178-213 balances by contig length): greedy longest-first bin packing"""
-    groups = [[] for _ in range(n)]
-    load = [0] * n
-    for name, ln in sorted(contigs, key=lambda x: -x[1]):
-        k = int(np.argmin(load)); groups[k].append((name, ln)); load[k] += ln
-    return groups
+    from elprep_b200 import multi
+    return multi.contig_groups(contigs, n)
 
 
 def cpu_pipeline(w, n_reads, threads):
