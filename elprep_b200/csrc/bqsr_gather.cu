@@ -525,17 +525,22 @@ __global__ void __launch_bounds__(256) ref_pack_kernel(const uint8_t* __restrict
     out[t] = (uint8_t)v;
 }
 
-// reads for the general kernel: eligible (c_len > 0) but not DF_LEAN
+// reads for the general kernel: eligible (c_len > 0) but not DF_LEAN.  One global atomic per block.
 __global__ void __launch_bounds__(256) gen_list_kernel(GatherArgs A) {
+    __shared__ uint32_t s_cnt, s_base;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool g = false;
     if (k < A.n) { const uint4 sc = __ldg(reinterpret_cast<const uint4*>(A.desc) + 3 * k + 1); g = (sc.y >> 16) != 0 && !(sc.z & DF_LEAN); }
     const unsigned b = __ballot_sync(FULL_MASK, g);
-    if (!b) return;
-    uint32_t base = 0;
-    if (lane_id() == 0) base = atomicAdd(A.gen_count, (uint32_t)__popc(b));
-    base = __shfl_sync(FULL_MASK, base, 0);
-    if (g) A.gen_list[base + __popc(b & lanemask_lt())] = (uint32_t)k;
+    uint32_t wbase = 0;
+    if (b && lane_id() == 0) wbase = atomicAdd(&s_cnt, (uint32_t)__popc(b));
+    wbase = __shfl_sync(FULL_MASK, wbase, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) s_base = atomicAdd(A.gen_count, s_cnt);
+    __syncthreads();
+    if (g) A.gen_list[s_base + wbase + __popc(b & lanemask_lt())] = (uint32_t)k;
 }
 
 // ---------------------------------------------------------------- kernel C: one warp per read, one lane per base

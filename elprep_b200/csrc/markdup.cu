@@ -82,15 +82,24 @@ __global__ void __launch_bounds__(256) adapt_kernel(uint64_t n, const uint16_t* 
                     wlo = wlo < 0 ? 0 : (wlo > 4 ? 4 : wlo); whi = whi < 0 ? 0 : (whi > 4 ? 4 : whi);
                     if (whi <= wlo) continue;
                     const uint32_t mhi = whi == 4 ? 0xffffffffu : ((1u << (8 * whi)) - 1), mlo = wlo == 0 ? 0u : ((1u << (8 * wlo)) - 1);
-                    const uint32_t x = w[t] & 0x7f7f7f7fu & mhi & ~mlo;
-                    bad |= __vcmpgtu4(x, 0x5d5d5d5du);
-                    s += __vsadu4(x & __vcmpgeu4(x, 0x0f0f0f0fu), 0u);
+                    const uint32_t x = w[t] & 0x7f7f7f7fu & mhi & ~mlo;                 // bytes < 128: the adds below cannot carry across bytes
+                    bad |= (x + 0x22222222u) & 0x80808080u;                               // some byte > 93
+                    const uint32_t ge15 = ((x + 0x71717171u) & 0x80808080u) >> 7;         // 1 per byte >= 15
+                    s = __dp4a(x & (ge15 * 0xffu), 0x01010101u, s);
                 }
             }
             // (lib, QNAME) hash for the mate join -- only needs to be a function of the bytes; equality is verified on bytes
             if (true_pair) {
                 const uint64_t n0 = qname_off[i], n1 = qname_off[i + 1];
-                for (uint64_t k = n0 + sub; k < n1; k += 8) h += mix64(((k - n0) << 8) | qname[k]);
+                // four bytes per step and lane; position-salted 32-bit mixes summed in 64 bits (order independent across lanes)
+                for (uint64_t k = n0 + 4 * sub; k < n1; k += 32) {
+                    uint32_t wv = 0;
+#pragma unroll
+                    for (int t = 0; t < 4; t++) if (k + t < n1) wv |= (uint32_t)qname[k + t] << (8 * t);
+                    uint32_t m = (wv ^ ((uint32_t)(k - n0) * 0x9E3779B1u)) * 0x85EBCA6Bu;
+                    m ^= m >> 15; m *= 0xC2B2AE35u; m ^= m >> 13;
+                    h += (uint64_t)m * 0x9E3779B97F4A7C15ull;
+                }
             }
         }
         // reduce over the 8 lanes of the group (all lanes of the warp take part)
