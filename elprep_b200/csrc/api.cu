@@ -5,6 +5,9 @@
 #include "ctx.h"
 
 int run_apply_kernel(elp_ctx* c, bool with_lut);
+#ifdef RS_TIMING
+void rs_dump_timing();
+#endif
 
 namespace {
 
@@ -402,6 +405,9 @@ int elp_debug_sort_u64(elp_ctx* c, uint64_t* keys, uint32_t* vals, uint64_t n, i
     CUDA_TRY(c, cudaMemcpyAsync(keys, in_b ? c->keys_b.p : c->keys_a.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(vals, in_b ? c->vals_b.p : c->vals_a.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+#ifdef RS_TIMING
+    rs_dump_timing();
+#endif
     return ELP_OK;
 }
 

@@ -209,8 +209,8 @@ int phase_coordinate_sort(elp_ctx* c, bool sort) {
             CUDA_TRY(c, c->bytes_tmp.reserve((size_t)m * 16 + 64, c->stream));
             uint64_t* ka = reinterpret_cast<uint64_t*>(c->bytes_tmp.p);
             uint64_t* kb = ka + m;
-            CUDA_TRY(c, c->mate.reserve(2 * m + 8, c->stream));
-            uint32_t* va = c->mate.p; uint32_t* vb = c->mate.p + m;
+            CUDA_TRY(c, c->mate.reserve(2 * m + 16, c->stream));
+            uint32_t* va = c->mate.p; uint32_t* vb = c->mate.p + ((m + 3) & ~(uint64_t)3);   // 16-byte aligned: the sort stages payloads with 16-byte async copies
             const int n_chunks = 3 + nq + 1;
             for (int ch = 0; ch < n_chunks; ch++) {
                 c->begin("tie_chunk_keys", (double)m * 32);

@@ -97,6 +97,13 @@ static __global__ void rs_scan_kernel(const uint32_t* __restrict__ ghist, uint32
     gofs[p * RADIX + d] = x - c + add;
 }
 
+#ifdef RS_TIMING
+// phase timestamps (clock64 of thread 0) of sampled tiles, read back by elp_debug_sort_u64
+static __device__ long long rs_tstamp[8 * 4096];
+#define RS_STAMP(k) do { if (tid == 0 && (tile & 1) == 0 && (tile >> 1) < 4096) rs_tstamp[(tile >> 1) * 8 + (k)] = clock64(); } while (0)
+#else
+#define RS_STAMP(k) do { } while (0)
+#endif
 // ---------------------------------------------------------------- one digit pass
 template <class K, int THREADS, int ITEMS, int MIN_CTAS>
 __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K* __restrict__ keys_in, K* __restrict__ keys_out,
@@ -108,6 +115,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K*
     uint32_t* warp_hist = reinterpret_cast<uint32_t*>(smem_raw);                // [WARPS][RADIX]
     K* sk = reinterpret_cast<K*>(smem_raw + (size_t)WARPS * RADIX * 4);         // [TILE]; reused for the payload
     uint32_t* sv = reinterpret_cast<uint32_t*>(sk);
+    uint32_t* stage_v = reinterpret_cast<uint32_t*>(smem_raw + (size_t)WARPS * RADIX * 4 + (size_t)TILE * sizeof(K));   // [TILE] payload in arrival order
     __shared__ uint32_t s_tile, digit_start[RADIX], gbase[RADIX], wsum[8];
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -116,6 +124,7 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K*
     for (int i = tid; i < WARPS * RADIX; i += THREADS) warp_hist[i] = 0;
     __syncthreads();
     const uint32_t tile = s_tile;
+    RS_STAMP(0);
     const uint64_t base = (uint64_t)tile * TILE;
     const uint32_t n_valid = (uint32_t)((n - base) < (uint64_t)TILE ? (n - base) : (uint64_t)TILE);
 
@@ -128,19 +137,48 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K*
         uint32_t t = wbase + j * 32;
         if (t < n_valid) key[j] = K::load(keys_in + base + t);
     }
+    // the payload is only needed after the keys are ranked and written: copy it to shared memory asynchronously now
+    // (16 bytes per request; a tile starts at a multiple of TILE elements, so the addresses are 16-byte aligned)
+    {
+        const uint32_t* vsrc = vals_in + base;
+        for (uint32_t q = tid * 4; q < (uint32_t)TILE; q += THREADS * 4) {
+            if (q + 4 <= n_valid) {
+                const uint32_t dsts = (uint32_t)__cvta_generic_to_shared(stage_v + q);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts), "l"(vsrc + q) : "memory");
+            } else {
+                for (uint32_t e = q; e < q + 4 && e < n_valid; e++) stage_v[e] = vsrc[e];
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    RS_STAMP(1);
     uint32_t* wh = warp_hist + warp * RADIX;
+#ifdef RS_PREFETCH_VALS
+    // the payload is only needed after the keys are ranked and scattered: pull its lines towards L1 now
+    if (lane < ITEMS && (wbase - lane + lane * 32) < n_valid) asm volatile("prefetch.global.L1 [%0];" ::"l"(vals_in + base + (wbase - lane) + lane * 32));
+#endif
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const bool valid = (wbase + j * 32) < n_valid;
         const uint32_t d = valid ? key[j].digit(shift, mask) : (0x100u + lane);   // invalid lanes match nobody
         const uint32_t peers = __match_any_sync(FULL_MASK, d);
+#ifdef RS_RANK_ATOM
         const uint32_t leader = __ffs(peers) - 1;
         uint32_t old = 0;
         if (valid && lane == leader) old = atomicAdd(&wh[d], (uint32_t)__popc(peers));   // shared atomics of one warp retire in issue order: no barrier between items
         old = __shfl_sync(FULL_MASK, old, leader);
+#else
+        // every peer reads the running count, then the leader adds the peer count (no atomic with a return value, no shuffle);
+        // __syncwarp orders the add before the next item's reads
+        const uint32_t old = valid ? wh[d] : 0u;
+        __syncwarp();
+        if (valid && (peers & lanemask_lt()) == 0) wh[d] = old + (uint32_t)__popc(peers);
+        __syncwarp();
+#endif
         rank[j] = old + __popc(peers & lanemask_lt());
     }
     __syncthreads();
+    RS_STAMP(2);
 
     // per digit: exclusive scan over warps, tile total, then exclusive scan over digits
     uint32_t total = 0;
@@ -156,51 +194,31 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K*
         digit_start[tid] = x - total;   // warp-local exclusive; warp sums added below
     }
     __syncthreads();
-    if (tid < RADIX) {
-        uint32_t add = 0;
-        for (unsigned i = 0; i < warp; i++) add += wsum[i];
-        const uint32_t dstart = digit_start[tid] + add;
-        digit_start[tid] = dstart;
-        // chained scan across tiles (decoupled look-back), one thread per digit
-        uint32_t excl = 0;
-        uint32_t* my = status + (uint64_t)tile * RADIX + tid;
-        // flag and value travel in ONE 32-bit word, so relaxed accesses are enough (no other data is published through it).
-        // The walk back over predecessor tiles issues LB independent loads per step: with hundreds of tiles in flight a
-        // one-load-at-a-time walk is a chain of serialized L2 round trips and caps the whole pass.
-        if (tile > 0) {
-            st_relaxed_u32(my, total | ST_PARTIAL);
+    // chained scan across tiles (decoupled look-back), one thread per digit.  Flag and value travel in ONE 32-bit word, so
+    // relaxed accesses are enough (no other data is published through it).  The walk back over predecessor tiles issues LB
+    // independent loads per step, and the first step is issued BEFORE the tile-local scatter so that its round trip overlaps it.
 #ifndef RS_LB
 #define RS_LB 8
 #endif
-            constexpr int LB = RS_LB;
-            int64_t t = (int64_t)tile - 1;
-            bool done = false;
-            while (!done) {
-                uint32_t sv[LB];
+    constexpr int LB = RS_LB;
+    uint32_t lb_first[LB];
+    uint32_t dstart = 0;
+    uint32_t* my = status + (uint64_t)tile * RADIX + tid;
+    if (tid < RADIX) {
+        uint32_t add = 0;
+        for (unsigned i = 0; i < warp; i++) add += wsum[i];
+        dstart = digit_start[tid] + add;
+        digit_start[tid] = dstart;
+        if (tile > 0) {
+            st_relaxed_u32(my, total | ST_PARTIAL);
 #pragma unroll
-                for (int j = 0; j < LB; j++) sv[j] = (t - j >= 0) ? ld_relaxed_u32(status + (uint64_t)(t - j) * RADIX + tid) : ST_INCLUSIVE;
-#pragma unroll
-                for (int j = 0; j < LB; j++) {
-                    if (done) break;
-                    uint32_t s = sv[j];
-                    while ((s >> 30) == 0) {   // predecessor not published yet
-#ifdef RS_NANOSLEEP
-                        __nanosleep(RS_NANOSLEEP);
-#endif
-                        s = ld_relaxed_u32(status + (uint64_t)(t - j) * RADIX + tid);
-                    }
-                    excl += s & ST_VALMASK;
-                    if ((s >> 30) == 2) done = true;
-                }
-                t -= LB;
-            }
+            for (int j = 0; j < LB; j++) lb_first[j] = ((int64_t)tile - 1 - j >= 0) ? ld_relaxed_u32(status + (uint64_t)(tile - 1 - j) * RADIX + tid) : ST_INCLUSIVE;
         }
-        st_relaxed_u32(my, ((excl + total) & ST_VALMASK) | ST_INCLUSIVE);
-        gbase[tid] = gofs[tid] + excl - dstart;   // modulo 2^32: final index = gbase[d] + tile-local sorted position
     }
     __syncthreads();
+    RS_STAMP(3);
 
-    // tile-local reorder through shared memory, then digit-contiguous (coalesced) global writes
+    // tile-local reorder through shared memory (needs only tile-local offsets)
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         if ((wbase + j * 32) < n_valid) {
@@ -209,7 +227,39 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K*
             sk[rank[j]] = key[j];
         }
     }
+    // finish the look-back
+    if (tid < RADIX) {
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int64_t t = (int64_t)tile - 1;
+            bool done = false, first = true;
+            while (!done) {
+                uint32_t svv[LB];
+#pragma unroll
+                for (int j = 0; j < LB; j++) svv[j] = first ? lb_first[j] : ((t - j >= 0) ? ld_relaxed_u32(status + (uint64_t)(t - j) * RADIX + tid) : ST_INCLUSIVE);
+                first = false;
+#pragma unroll
+                for (int j = 0; j < LB; j++) {
+                    if (done) break;
+                    uint32_t sx = svv[j];
+                    while ((sx >> 30) == 0) {   // predecessor not published yet
+#ifdef RS_NANOSLEEP
+                        __nanosleep(RS_NANOSLEEP);
+#endif
+                        sx = ld_relaxed_u32(status + (uint64_t)(t - j) * RADIX + tid);
+                    }
+                    excl += sx & ST_VALMASK;
+                    if ((sx >> 30) == 2) done = true;
+                }
+                t -= LB;
+            }
+        }
+        st_relaxed_u32(my, ((excl + total) & ST_VALMASK) | ST_INCLUSIVE);
+        gbase[tid] = gofs[tid] + excl - dstart;   // modulo 2^32: final index = gbase[d] + tile-local sorted position
+    }
+    // digit-contiguous (coalesced) global writes
     __syncthreads();
+    RS_STAMP(4);
     uint32_t dst[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
@@ -220,16 +270,20 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K*
             keys_out[dst[k]] = kk;
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    RS_STAMP(5);
 #pragma unroll
     for (int j = 0; j < ITEMS; j++)
-        if ((wbase + j * 32) < n_valid) sv[rank[j]] = ld_stream_u32(vals_in + base + wbase + j * 32);   // payload is loaded late: fewer live registers -> more CTAs per SM
+        if ((wbase + j * 32) < n_valid) sv[rank[j]] = stage_v[wbase + j * 32];
     __syncthreads();
+    RS_STAMP(6);
 #pragma unroll
     for (int k = 0; k < ITEMS; k++) {
         const uint32_t s = tid + k * THREADS;
         if (s < n_valid) vals_out[dst[k]] = sv[s];
     }
+    RS_STAMP(7);
 }
 
 // ---------------------------------------------------------------- host driver
@@ -251,7 +305,7 @@ template <> struct Cfg<K64> { static constexpr int THREADS = RS64_THREADS, ITEMS
 template <> struct Cfg<K128> { static constexpr int THREADS = 256, ITEMS = 8, MIN_CTAS = 4; };
 
 template <class K> inline size_t tile_size() { return (size_t)Cfg<K>::THREADS * Cfg<K>::ITEMS; }
-template <class K> inline size_t smem_bytes() { return (size_t)(Cfg<K>::THREADS / 32) * RADIX * 4 + tile_size<K>() * sizeof(K); }
+template <class K> inline size_t smem_bytes() { return (size_t)(Cfg<K>::THREADS / 32) * RADIX * 4 + tile_size<K>() * sizeof(K) + tile_size<K>() * 4; }
 template <class K> inline size_t status_bytes_needed(uint64_t n, int key_bits) {
     Plan p = make_plan(key_bits);
     uint64_t tiles = (n + tile_size<K>() - 1) / tile_size<K>();

@@ -44,6 +44,7 @@ int radix_sort_impl(elp_ctx* c, K* ka, K* kb, uint32_t* va, uint32_t* vb, uint64
         c->end();
         LAUNCH_CHECK(c);
     }
+    if ((reinterpret_cast<uintptr_t>(va) | reinterpret_cast<uintptr_t>(vb)) & 15) return c->fail(E_INVAL, "radix sort: payload buffers must be 16-byte aligned");
     auto kern = rs_onesweep_kernel<K, Cfg<K>::THREADS, Cfg<K>::ITEMS, Cfg<K>::MIN_CTAS>;
     const size_t smem = smem_bytes<K>();
     static bool attr_set = false;   // per template instantiation
@@ -148,3 +149,19 @@ int radix_sort_u128(elp_ctx* c, uint64_t* ka, uint64_t* kb, uint32_t* va, uint32
 }
 int exclusive_scan_u32_to_u64(elp_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n) { return scan_impl<uint32_t>(c, in, out, n, 0); }
 int exclusive_scan_u64(elp_ctx* c, const uint64_t* in, uint64_t* out, uint64_t n, uint64_t base) { return scan_impl<uint64_t>(c, in, out, n, base); }
+
+#ifdef RS_TIMING
+#include <cstdio>
+// prints the mean clock cycles between the phase stamps of the sampled tiles of the LAST pass
+void rs_dump_timing() {
+    static long long h[8 * 4096];
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h, rs::rs_tstamp, sizeof h);
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0}; int cnt = 0;
+    for (int t = 8; t < 4096; t++) { const long long* p = h + 8 * t; if (p[7] <= p[0] || p[0] == 0) continue; for (int k = 0; k < 7; k++) acc[k] += (double)(p[k + 1] - p[k]); cnt++; }
+    const char* names[7] = {"load-issue", "rank", "scan+lookback", "scatter-smem", "write-keys", "load-vals", "write-vals"};
+    fprintf(stderr, "onesweep phase cycles over %d sampled tiles:", cnt);
+    for (int k = 0; k < 7; k++) fprintf(stderr, "  %s %.0f", names[k], cnt ? acc[k] / cnt : 0.0);
+    fprintf(stderr, "\n");
+}
+#endif

@@ -8,12 +8,15 @@ import csv, io, re, subprocess, sys, tempfile, os, glob
 
 rep, kre, lib = sys.argv[1:4]
 minpct = float(sys.argv[4]) if len(sys.argv) > 4 else 0.5
+mangled_has = sys.argv[5].split(",") if len(sys.argv) > 5 else []   # extra substrings the mangled name must contain (template args)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kre, "--print-source", "sass"],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 # may contain several launches: keep the first
 start = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"]
-seg = rows[start[0]:(start[1] if len(start) > 1 else len(rows))]
+start = [i for i in start if all(x in rows[i][1] for x in (sys.argv[5].split(",") if len(sys.argv) > 5 else []))] or start
+nxt = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and i > start[0]]
+seg = rows[start[0]:(nxt[0] if nxt else len(rows))]
 kname = seg[0][1]
 hdr = seg[1]
 ci, cs = hdr.index("Instructions Executed"), hdr.index("# Samples")
@@ -21,7 +24,7 @@ inst = [(r[1].strip(), int(r[ci] or 0), int(r[cs] or 0)) for r in seg[2:] if len
 
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-short = re.sub(r"\(.*", "", kname).split("::")[-1].split("<")[0]
+short = kname.split("(")[0].split("<")[0].split("::")[-1].split()[-1]
 lines = None
 for f in glob.glob(tmp + "/*.cubin"):
     txt = subprocess.run(["nvdisasm", "-g", "-c", f], capture_output=True, text=True).stdout
@@ -30,7 +33,7 @@ for f in glob.glob(tmp + "/*.cubin"):
     cur, out, active = None, [], False
     for l in txt.splitlines():
         if l.startswith(".text."):
-            active = short in l and (not out)
+            active = short in l and all(x in l for x in mangled_has) and (not out)
             continue
         if not active:
             continue
