@@ -177,7 +177,7 @@ struct __align__(16) ReadDesc {
     uint32_t ovf;             // slot of the 512-bit skip bitmask when more than 4 known-site ranges hit the read
     uint16_t skip[4][2];      // inclusive [first,last] clipped read coordinates masked by known sites
 };                            // 48 bytes = three 16-byte loads: location | scalars | skip ranges
-constexpr uint8_t DF_REVERSED = 1, DF_LAST = 2, DF_SINGLE_M = 4, DF_SKIP_OVF = 8, DF_LEAN = 16;
+constexpr uint8_t DF_REVERSED = 1, DF_LAST = 2, DF_SINGLE_M = 4, DF_SKIP_OVF = 8, DF_LEAN = 16, DF_CHUNKG = 32;   // DF_CHUNKG: chunk kernel with a per-lane CIGAR walk
 constexpr int OVF_WORDS = 16;   // 512 bits
 
 struct GatherArgs {
@@ -192,7 +192,8 @@ struct GatherArgs {
     TableGeom geom; unsigned long long* tables; uint32_t* err;
     ReadDesc* desc; uint32_t* ovf_bits; uint32_t* ovf_count; uint32_t ovf_cap;
     const uint8_t* const* refnib;    // per contig: reference base codes, 4 bits per base, low nibble first
-    uint32_t* gen_list; uint32_t* gen_count;   // reads that take the general (warp per read) kernel
+    uint32_t* gen_list; uint32_t* gen_count;   // [0]: reads for the warp-per-read fallback kernel, list grows up from gen_list[0]
+    uint32_t* cg_list;                         // [1] of gen_count: insertion/deletion reads for the chunk kernel's GEN variant
     int lanes_per_read;              // chunk kernel: lanes (16-base chunks) reserved per read
     // shared-memory privatisation: observation counters of the frequent QUAL values live in shared memory
     int8_t qslot[94]; uint8_t slot_q[94]; int n_slots, Lc;
@@ -311,6 +312,7 @@ __global__ void __launch_bounds__(128) bqsr_prep_kernel(GatherArgs A) {
     // chunk kernel: one M run, every cycle inside --max-cycle (|cycle| <= L), inside the contig, fits the lanes of a read
     if ((d.flags & DF_SINGLE_M) && !(d.flags & DF_SKIP_OVF) && L <= A.geom.max_cycle && L <= CHUNK * A.lanes_per_read &&
         (uint64_t)(a.pos - 1) + (uint64_t)L <= A.ref_len[refid]) d.flags |= DF_LEAN;
+    else if (!(d.flags & DF_SKIP_OVF) && L <= A.geom.max_cycle && L <= CHUNK * A.lanes_per_read) d.flags |= DF_CHUNKG;
     done();
 }
 
@@ -356,7 +358,8 @@ struct ChunkSmem { uint32_t obs, mis, qslot; };   // shared-window byte addresse
 #ifndef CHUNK_MINB
 #define CHUNK_MINB 4
 #endif
-__global__ void __launch_bounds__(256, CHUNK_MINB) bqsr_chunk_kernel(GatherArgs A) {
+template <bool GEN>   // GEN: reads come from a list and may contain insertions / deletions (reference window per lane from the CIGAR)
+__global__ void __launch_bounds__(256, CHUNK_MINB) bqsr_chunk_kernel(GatherArgs A, const uint32_t* __restrict__ list, uint32_t n_list) {
     extern __shared__ uint32_t sm_tab[];
     // QUAL -> row of the CTA's tables: bits 0..5 = shared-memory slot, or n_slots = the trash row (updates that must not
     // count land there, which keeps the per-base code free of predicates); bit 6: QUAL < 6 (never counted, bqsr.go:506);
@@ -395,28 +398,71 @@ __global__ void __launch_bounds__(256, CHUNK_MINB) bqsr_chunk_kernel(GatherArgs 
     const uint4* dbase = reinterpret_cast<const uint4*>(A.desc);
     uint32_t errbits = 0;
     // descriptors are fetched one step ahead
+    const uint64_t n_items = GEN ? (uint64_t)n_list : A.n;
+    auto read_of = [&](uint64_t item) -> uint64_t { return GEN ? (uint64_t)__ldg(list + item) : item; };
     uint64_t k = wid * rpw + (uint64_t)r;
     uint4 nloc = make_uint4(0, 0, 0, 0), nsc = make_uint4(0, 0, 0, 0);
-    if (lane_used && k < A.n) { nloc = __ldg(dbase + 3 * k); nsc = __ldg(dbase + 3 * k + 1); }
-    for (uint64_t k0 = wid * rpw; k0 < A.n; k0 += warps * rpw) {
+    uint64_t nread = 0;
+    if (lane_used && k < n_items) { nread = read_of(k); nloc = __ldg(dbase + 3 * nread); nsc = __ldg(dbase + 3 * nread + 1); }
+    for (uint64_t k0 = wid * rpw; k0 < n_items; k0 += warps * rpw) {
         const uint4 loc = nloc, sc = nsc;
-        const uint64_t kcur = k0 + (uint64_t)r, knext = kcur + warps * rpw;
+        const uint64_t item = k0 + (uint64_t)r, inext = item + warps * rpw;
+        const uint64_t kcur = nread;
+        const bool have = lane_used && item < n_items;
         nloc = make_uint4(0, 0, 0, 0); nsc = nloc;
-        if (lane_used && knext < A.n) { nloc = __ldg(dbase + 3 * knext); nsc = __ldg(dbase + 3 * knext + 1); }
+        if (lane_used && inext < n_items) { nread = read_of(inext); nloc = __ldg(dbase + 3 * nread); nsc = __ldg(dbase + 3 * nread + 1); }
         const uint32_t flags = sc.z & 0xff;
-        const int L = (lane_used && kcur < A.n && (flags & DF_LEAN)) ? (int)(sc.y >> 16) : 0;   // 0: nothing to do for this lane group
+        const int L = (have && (flags & (GEN ? DF_CHUNKG : DF_LEAN))) ? (int)(sc.y >> 16) : 0;   // 0: nothing to do for this lane group
         const int i0 = c * CHUNK, nb = min(max(L - i0, 0), CHUNK);                                // bases of this chunk
         const bool rev = flags & DF_REVERSED;
         // ---- loads ----
         uint32_t Q[4] = {0, 0, 0, 0};
-        unsigned long long C = 0, R = 0;
+        unsigned long long C = 0, R = 0, pastf = 0;
         if (nb > 0) {
             const uint64_t qloc = ((uint64_t)loc.y << 32) | loc.x, nl = ((uint64_t)loc.w << 32) | loc.z;
             const uint32_t refid = (uint32_t)(qloc >> 40);
             load16_unaligned(A.qual + (qloc & ((1ull << 40) - 1)) + (uint64_t)i0, Q);
             const unsigned long long nibs = load16_nibbles_bam(A.seq, nl + (uint64_t)i0);
-            R = load16_nibbles_le(A.refnib[refid], (uint64_t)((int64_t)(int32_t)sc.x - 1 + i0));
             C = (unsigned long long)codes_of((uint32_t)nibs) | ((unsigned long long)codes_of((uint32_t)(nibs >> 32)) << 32);
+            if (!GEN) R = load16_nibbles_le(A.refnib[refid], (uint64_t)((int64_t)(int32_t)sc.x - 1 + i0));
+            else {
+                // computeSnpEvents (bqsr.go:254-285) over the ORIGINAL alignment (kept bases keep their positions under hard
+                // clipping): find the operation holding the chunk's first base; a chunk inside one M run is one window load,
+                // a chunk that touches an insertion / deletion takes its reference codes base by base
+                const uint64_t coff = A.cigar_off[kcur]; const int nc = (int)A.ncigar[kcur];
+                const int oi0 = (int)(sc.y & 0xffff) + i0;                    // read offset in the stored (unclipped) read
+                int ri = 0, ci = 0, oplen = 0, opk = -1; int64_t j = (int64_t)A.pos[kcur] - 1;
+                for (; ci < nc; ci++) {
+                    const uint32_t op = __ldg(A.cigar + coff + ci); const int o = op_of(op), ln = len_of(op);
+                    if (cons_read(o)) { if (oi0 < ri + ln) { opk = o; oplen = ln; break; } ri += ln; }
+                    if (o == 0 || o == 7 || o == 8 || o == 2 || o == 3) j += ln;
+                }
+                const int64_t reflen = (int64_t)A.ref_len[refid];
+                const bool mtype = opk == 0 || opk == 7 || opk == 8;
+                if (mtype && oi0 + nb <= ri + oplen && j + (oi0 - ri) + nb <= reflen) R = load16_nibbles_le(A.refnib[refid], (uint64_t)(j + (oi0 - ri)));
+                else {
+                    const uint8_t* rn = A.refnib[refid];
+                    int rem = opk < 0 ? 0 : ri + oplen - oi0;                   // bases left in the current operation
+                    int64_t jj = j + (mtype ? (oi0 - ri) : 0);
+                    bool m = mtype;
+                    for (int b = 0; b < nb; b++) {
+                        while (rem == 0 && ci + 1 < nc) {                      // next read-consuming operation (deletions move the reference)
+                            ci++;
+                            const uint32_t op = __ldg(A.cigar + coff + ci); const int o = op_of(op), ln = len_of(op);
+                            if (o == 2 || o == 3) { jj += ln; continue; }
+                            if (cons_read(o)) { rem = ln; m = (o == 0 || o == 7 || o == 8); }
+                        }
+                        unsigned long long rc = (C >> (4 * b)) & 15ull;         // no reference base (insertion): never a mismatch
+                        if (m) {
+                            if (jj >= reflen) pastf |= 1ull << (4 * b);
+                            else rc = (unsigned long long)((__ldg(rn + (jj >> 1)) >> (4 * (int)(jj & 1))) & 15u);
+                            jj++;
+                        }
+                        R |= rc << (4 * b);
+                        rem--;
+                    }
+                }
+            }
         }
         if (nb < CHUNK) { const unsigned long long inlen = range16(0, nb - 1); C = (C & (inlen * 15ull)) | ((ONES & ~inlen) << 3); }   // codes past the read end: 8
         // ---- low-quality tails (computeStrandedClippedSeq, bqsr.go:312-331): first / last base with QUAL > 2 ----
@@ -438,7 +484,7 @@ __global__ void __launch_bounds__(256, CHUNK_MINB) bqsr_chunk_kernel(GatherArgs 
         unsigned long long skipf = 0;
         const uint32_t n_skip = (sc.z >> 16) & 0xff;
         if (n_skip) {
-            const uint4 sk = __ldg(dbase + 3 * kcur + 2);
+            const uint4 sk = __ldg(dbase + 3 * kcur + 2);   // (kcur: read index of this lane group)
             const uint32_t skv[4] = {sk.x, sk.y, sk.z, sk.w};
 #pragma unroll
             for (int t = 0; t < 4; t++) if (t < (int)n_skip) skipf |= range16((int)(skv[t] & 0xffff) - i0, (int)(skv[t] >> 16) - i0);
@@ -447,6 +493,7 @@ __global__ void __launch_bounds__(256, CHUNK_MINB) bqsr_chunk_kernel(GatherArgs 
         const unsigned long long okc = counted & ~((Pn | C) >> 3) & range16(wlo - i0, whi - i0);
         const unsigned long long X = C ^ R;
         const unsigned long long snpf = (X | (X >> 1) | (X >> 2) | (X >> 3)) & counted;         // computeSnpEvents, bqsr.go:254-285
+        if (GEN && (pastf & counted)) errbits |= DERR_REFEND;                                   // a counted base beyond the end of its contig
         if (counted) {
         // ---- table updates ----
         const uint32_t cov = (sc.z >> 8) & 0xff;
@@ -525,22 +572,29 @@ __global__ void __launch_bounds__(256) ref_pack_kernel(const uint8_t* __restrict
     out[t] = (uint8_t)v;
 }
 
-// reads for the general kernel: eligible (c_len > 0) but not DF_LEAN.  One global atomic per block.
+// work lists of the eligible reads that are not DF_LEAN: DF_CHUNKG reads (insertions / deletions) for the chunk kernel's GEN
+// variant, everything else for the warp-per-read fallback.  One global atomic per block and list.
 __global__ void __launch_bounds__(256) gen_list_kernel(GatherArgs A) {
-    __shared__ uint32_t s_cnt, s_base;
-    if (threadIdx.x == 0) s_cnt = 0;
+    __shared__ uint32_t s_cnt[2], s_base[2];
+    if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool g = false;
-    if (k < A.n) { const uint4 sc = __ldg(reinterpret_cast<const uint4*>(A.desc) + 3 * k + 1); g = (sc.y >> 16) != 0 && !(sc.z & DF_LEAN); }
-    const unsigned b = __ballot_sync(FULL_MASK, g);
-    uint32_t wbase = 0;
-    if (b && lane_id() == 0) wbase = atomicAdd(&s_cnt, (uint32_t)__popc(b));
-    wbase = __shfl_sync(FULL_MASK, wbase, 0);
+    int which = -1;
+    if (k < A.n) { const uint4 sc = __ldg(reinterpret_cast<const uint4*>(A.desc) + 3 * k + 1); if ((sc.y >> 16) != 0 && !(sc.z & DF_LEAN)) which = (sc.z & DF_CHUNKG) ? 1 : 0; }
+    uint32_t wbase = 0, before = 0;
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+        const unsigned b = __ballot_sync(FULL_MASK, which == l);
+        uint32_t wb = 0;
+        if (b && lane_id() == 0) wb = atomicAdd(&s_cnt[l], (uint32_t)__popc(b));
+        wb = __shfl_sync(FULL_MASK, wb, 0);
+        if (which == l) { wbase = wb; before = __popc(b & lanemask_lt()); }
+    }
     __syncthreads();
-    if (threadIdx.x == 0 && s_cnt) s_base = atomicAdd(A.gen_count, s_cnt);
+    if (threadIdx.x < 2 && s_cnt[threadIdx.x]) s_base[threadIdx.x] = atomicAdd(A.gen_count + threadIdx.x, s_cnt[threadIdx.x]);
     __syncthreads();
-    if (g) A.gen_list[s_base + wbase + __popc(b & lanemask_lt())] = (uint32_t)k;
+    if (which == 0) A.gen_list[s_base[0] + wbase + before] = (uint32_t)k;
+    if (which == 1) A.cg_list[s_base[1] + wbase + before] = (uint32_t)k;
 }
 
 // ---------------------------------------------------------------- kernel C: one warp per read, one lane per base
@@ -775,15 +829,15 @@ int phase_bqsr_gather(elp_ctx* c) {
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         // descriptors (32 B/read) and the overflow skip bitmasks live in scratch buffers that are free in this phase
         CUDA_TRY(c, c->keys_a.reserve(n * 6 + 8, c->stream));
-        CUDA_TRY(c, c->vals_b.reserve(n + 8, c->stream));
-        A.gen_list = c->vals_b.p;
+        CUDA_TRY(c, c->vals_b.reserve(2 * n + 16, c->stream));
+        A.gen_list = c->vals_b.p; A.cg_list = c->vals_b.p + n + 8;
         A.desc = reinterpret_cast<ReadDesc*>(c->keys_a.p);
         A.ovf_cap = (uint32_t)std::min<uint64_t>(n, (n >> 4) + 4096);
         CUDA_TRY(c, c->vals_a.reserve((size_t)A.ovf_cap * OVF_WORDS + 8, c->stream));
         A.ovf_bits = c->vals_a.p;
-        A.ovf_count = c->scan_tmp.p;   // two u32 (overflow slots, general-kernel reads), zeroed below
+        A.ovf_count = c->scan_tmp.p;   // three u32 (overflow slots, fallback reads, GEN chunk reads), zeroed below
         A.gen_count = c->scan_tmp.p + 1;
-        CUDA_TRY(c, cudaMemsetAsync(A.ovf_count, 0, 8, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(A.ovf_count, 0, 12, c->stream));
         c->begin("bqsr_prep", (double)n * (4 * 7 + 2 + 1 + 8 + 8 + 4 + 48) + (double)c->n_cigar * 4);
         bqsr_prep_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(A);
         c->end(); LAUNCH_CHECK(c);
@@ -793,13 +847,22 @@ int phase_bqsr_gather(elp_ctx* c) {
         const uint64_t rpw = 32 / A.lanes_per_read, steps = (n + rpw - 1) / rpw;
         uint64_t grid = std::min<uint64_t>((steps + 7) / 8, (uint64_t)sms * CHUNK_MINB);
         grid = std::max<uint64_t>(grid, (n + (4u << 20) - 1) / (4u << 20));   // <= 4 M reads per CTA keeps the 32-bit shared counters far from overflow
-        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
         c->begin("bqsr_gather", bytes);
-        bqsr_chunk_kernel<<<(unsigned)grid, 256, smem, c->stream>>>(A);
+        bqsr_chunk_kernel<false><<<(unsigned)grid, 256, smem, c->stream>>>(A, nullptr, 0);
         c->end(); LAUNCH_CHECK(c);
-        uint32_t n_gen = 0;
-        CUDA_TRY(c, cudaMemcpyAsync(&n_gen, A.gen_count, 4, cudaMemcpyDeviceToHost, c->stream));
+        uint32_t cnt2[2] = {0, 0};
+        CUDA_TRY(c, cudaMemcpyAsync(cnt2, A.gen_count, 8, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        const uint32_t n_gen = cnt2[0], n_cg = cnt2[1];
+        if (n_cg) {
+            const uint64_t steps_g = ((uint64_t)n_cg + rpw - 1) / rpw;
+            const uint64_t grid_cg = std::min<uint64_t>((steps_g + 7) / 8, (uint64_t)sms * CHUNK_MINB);
+            c->begin("bqsr_gather_indel", (double)n_cg * (48 + 19 + 8 + 225 + 75));
+            bqsr_chunk_kernel<true><<<(unsigned)grid_cg, 256, smem, c->stream>>>(A, A.cg_list, n_cg);
+            c->end(); LAUNCH_CHECK(c);
+        }
         if (n_gen) {
             const size_t smem_g = (size_t)c->geom.n_cov * A.n_slots * (2 * Lc + 1 + 16) * 4 * 2;
             const uint64_t grid_g = std::min<uint64_t>(((uint64_t)n_gen + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (uint64_t)sms * 4);
