@@ -243,7 +243,17 @@ def main():
     if dom[0]:
         k = dom[1]
         ach = k["alg_bytes"] / (k["ms"] / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+        # DRAM bytes per launch of that kernel from an `ncu --set full` capture of this same workload (profiles/*_traffic.json,
+        # written by hand from the capture named in it); only used when the capture was taken on the same number of reads
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            ent = tr["kernels"].get(dom[0])
+            if ent and abs(tr["reads"] - n_reads) <= 0.01 * n_reads and world == 1:
+                traffic = ent["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "launches": k["launches"], "avg_launch_ms": k["ms"] / max(1, k["launches"]), "alg_bytes_per_launch": k["alg_bytes"] / max(1, k["launches"])}
     kern = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                 "GBps": (v["alg_bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["alg_bytes"] > 0 else None} for n, v in sorted(stats.items(), key=lambda kv: -kv[1]["ms"])}
