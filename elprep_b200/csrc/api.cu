@@ -88,6 +88,7 @@ int elp_create(const elp_config* cfg, elp_ctx** out) {
     std::map<std::string, int> libs, covs;
     for (int i = 0; i < c->n_rg; i++) {
         if (!cfg->rg_id || !cfg->rg_id[i]) { c->err = "Missing mandatory ID entry in an @RG line in a SAM file header."; return bail(ELP_EINVAL); }
+        c->rg_ids.push_back(cfg->rg_id[i]);
         const char* lb = cfg->rg_lb ? cfg->rg_lb[i] : nullptr;
         if (lb) { auto it = libs.find(lb); if (it == libs.end()) { it = libs.emplace(lb, (int)libs.size()).first; c->lib_names.push_back(lb); } c->rg_lib.push_back(it->second); } else c->rg_lib.push_back(-1);
         const char* pu = cfg->rg_pu ? cfg->rg_pu[i] : nullptr;
@@ -129,11 +130,11 @@ void elp_destroy(elp_ctx* c) {
     for (auto p : c->d_refnib_raw) if (p) cudaFree(p);
     for (auto p : c->d_sites) if (p) cudaFree(p);
     void* singles[] = {c->d_rg_lib, c->d_rg_cov, c->d_contig_len, c->d_ranges, c->d_err, (void*)c->d_ref_ptrs, (void*)c->d_refnib_ptrs, c->d_ref_len, (void*)c->d_site_ptrs, c->d_n_sites, c->d_tables,
-                       c->d_lut, c->d_cov_exists, c->d_opt_ctr, c->d_opt_hist, c->d_opt_ovf, c->d_opt_small, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
+                       c->d_lut, c->d_cov_exists, c->d_opt_ctr, c->d_opt_hist, c->d_opt_ovf, c->d_opt_small, c->d_rg_names, c->d_rg_name_off, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
     for (void* p : singles) if (p) cudaFree(p);
     c->refid.release(); c->pos.release(); c->nref.release(); c->pnext.release(); c->tlen.release(); c->rg.release(); c->flag.release(); c->mapq.release();
     c->qname_off.release(); c->cigar_off.release(); c->qual_off.release(); c->seq_off.release(); c->qname.release(); c->seq.release(); c->qual.release(); c->cigar.release();
-    c->lseq_stage.release(); c->off_stage.release(); c->upos.release(); c->score.release(); c->qhash.release(); c->keys_a.release(); c->keys_b.release();
+    c->bam_raw.release(); c->bam_off.release(); c->lseq_stage.release(); c->off_stage.release(); c->upos.release(); c->score.release(); c->qhash.release(); c->keys_a.release(); c->keys_b.release();
     c->vals_a.release(); c->vals_b.release(); c->mate.release(); c->pair_a.release(); c->pair_b.release(); c->scan_tmp.release(); c->scan_blk.release(); c->bytes_tmp.release();
     c->perm.release(); c->s_refid.release(); c->s_pos.release(); c->s_nref.release(); c->s_pnext.release(); c->s_tlen.release(); c->s_rg.release(); c->s_lseq.release();
     c->s_flag.release(); c->s_mapq.release(); c->s_qual_off.release(); c->s_seq_off.release(); c->s_cigar_off.release(); c->s_out_off.release(); c->s_ncigar.release(); c->qual_out.release();

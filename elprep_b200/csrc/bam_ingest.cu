@@ -1,0 +1,217 @@
+// bam_ingest.cu -- BAM alignment records straight into the device columns (replaces the host-side
+// parseBamAlignment, sam/bam-files.go:314-400, for the fields this path uses).
+//
+// The caller hands over the decompressed BAM record bytes as they sit in the file (each record preceded by its 4-byte
+// block_size) plus the byte offset of every record.  Two kernels:
+//   bam_fixed_kernel  one thread per record: the fixed-offset little-endian fields (:300-312) -> refid, pos (+1), flag, mapq,
+//                     nref, pnext (+1), tlen columns; the lengths of the four variable parts; the RG:Z tag located by walking
+//                     the typed optional fields (sam/bam-files.go optionalBAMFieldParseTable) and matched against @RG IDs
+//   bam_copy_kernel   one warp per record: QNAME bytes (without the NUL), CIGAR words (already `len<<4|op`), SEQ nibbles
+//                     and QUAL bytes (phred without +33) are byte-for-byte the device layout -> four segmented copies
+// Offsets come from device prefix sums of the lengths.  Not handled (error return): the CG:B long-CIGAR convention (:376-392),
+// an RG:Z value that is not an @RG ID of the header.
+#include "ctx.h"
+#include "../../include/elprep_b200.h"
+
+namespace {
+
+inline unsigned nblk(uint64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+__device__ __forceinline__ uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+__device__ __forceinline__ uint32_t rd16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+struct BamArgs {
+    uint64_t n, n0;                       // records in this call, reads already in the context
+    const uint8_t* raw; const uint64_t* rec_off;
+    int32_t *refid, *pos, *nref, *pnext, *tlen, *rg; uint16_t* flag; uint8_t* mapq;
+    uint32_t *len_qname, *len_cigar, *len_seq, *len_qual;   // [n] lengths, scanned afterwards
+    const uint8_t* rg_names; const uint32_t* rg_name_off; int n_rg; int n_contigs;
+    uint32_t* err;
+};
+
+// fixed part: block_size(4) refID(4) pos(4) l_read_name(1) mapq(1) bin(2) n_cigar_op(2) flag(2) l_seq(4) next_refID(4) next_pos(4) tlen(4)
+constexpr int BAM_FIXED = 36;
+
+__global__ void __launch_bounds__(256) bam_fixed_kernel(BamArgs A) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    const uint8_t* r = A.raw + A.rec_off[i];
+    const uint64_t rec_len = A.rec_off[i + 1] - A.rec_off[i];
+    uint32_t bad = 0;
+    if (rec_len < BAM_FIXED) { atomicOr(A.err, DERR_BAM); A.len_qname[i] = A.len_cigar[i] = A.len_seq[i] = A.len_qual[i] = 0; return; }
+    const uint32_t block_size = rd32(r);
+    if ((uint64_t)block_size + 4 != rec_len) bad = 1;
+    const int32_t refid = (int32_t)rd32(r + 4), pos = (int32_t)rd32(r + 8);
+    const uint32_t l_name = r[12], mapq = r[13], n_cig = rd16(r + 16), flag = rd16(r + 18);
+    const int32_t l_seq = (int32_t)rd32(r + 20), nref = (int32_t)rd32(r + 24), pnext = (int32_t)rd32(r + 28), tlen = (int32_t)rd32(r + 32);
+    const uint64_t var = (uint64_t)l_name + 4ull * n_cig + (uint64_t)((l_seq + 1) >> 1) + (uint64_t)max(l_seq, 0);
+    if (l_name < 1 || l_seq < 0 || BAM_FIXED + var > rec_len || refid >= A.n_contigs || nref >= A.n_contigs) bad = 1;
+    const uint64_t k = A.n0 + i;
+    A.refid[k] = refid < 0 ? -1 : refid; A.pos[k] = pos + 1; A.flag[k] = (uint16_t)flag; A.mapq[k] = (uint8_t)mapq;
+    A.nref[k] = nref < 0 ? -1 : nref; A.pnext[k] = pnext + 1; A.tlen[k] = tlen;
+    int32_t rg = -1;
+    if (!bad) {
+        // optional fields: tag[2] type[1] value (sam/bam-files.go:369-397)
+        uint64_t x = BAM_FIXED + var;
+        while (x + 3 <= rec_len) {
+            const uint8_t t0 = r[x], t1 = r[x + 1], ty = r[x + 2];
+            x += 3;
+            uint64_t sz = 0; bool str = false;
+            switch (ty) {
+                case 'A': case 'c': case 'C': sz = 1; break;
+                case 's': case 'S': sz = 2; break;
+                case 'i': case 'I': case 'f': sz = 4; break;
+                case 'Z': case 'H': str = true; break;
+                case 'B': {
+                    if (x + 5 > rec_len) { bad = 1; break; }
+                    const uint8_t sub = r[x]; const uint64_t cnt = rd32(r + x + 1);
+                    const uint64_t es = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : ((sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0));
+                    if (!es) bad = 1;
+                    if (t0 == 'C' && t1 == 'G') bad = 2;     // long-CIGAR convention: not supported here
+                    sz = 5 + cnt * es; break;
+                }
+                default: bad = 1;
+            }
+            if (bad) break;
+            if (str) {
+                uint64_t e = x;
+                while (e < rec_len && r[e] != 0) e++;
+                if (e >= rec_len) { bad = 1; break; }
+                if (t0 == 'R' && t1 == 'G' && ty == 'Z') {
+                    rg = -2;                                   // present but (so far) unknown
+                    for (int g = 0; g < A.n_rg; g++) {
+                        const uint32_t a = A.rg_name_off[g], b = A.rg_name_off[g + 1];
+                        if ((uint64_t)(b - a) != e - x) continue;
+                        bool same = true;
+                        for (uint32_t q = 0; q < b - a && same; q++) same = A.rg_names[a + q] == r[x + q];
+                        if (same) { rg = g; break; }
+                    }
+                }
+                x = e + 1;
+            } else { if (x + sz > rec_len) { bad = 1; break; } x += sz; }
+        }
+        if (x != rec_len && !bad) bad = 1;
+    }
+    if (rg == -2) { atomicOr(A.err, DERR_BAM_RG); rg = -1; }
+    if (bad) atomicOr(A.err, bad == 2 ? DERR_BAM_CG : DERR_BAM);
+    A.rg[k] = rg;
+    A.len_qname[i] = bad ? 0 : l_name - 1; A.len_cigar[i] = bad ? 0 : n_cig;
+    A.len_seq[i] = bad ? 0 : (uint32_t)((l_seq + 1) >> 1); A.len_qual[i] = bad ? 0 : (uint32_t)l_seq;
+}
+
+struct CopyArgs {
+    uint64_t n, n0;
+    const uint8_t* raw; const uint64_t* rec_off;
+    const uint64_t *qname_off, *cigar_off, *seq_off, *qual_off;   // arena-global, indexed n0 + i
+    uint8_t* qname; uint32_t* cigar; uint8_t* seq; uint8_t* qual;
+};
+
+__global__ void __launch_bounds__(256) bam_copy_kernel(CopyArgs A) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= A.n) return;
+    const uint64_t k = A.n0 + i;
+    const uint8_t* r = A.raw + A.rec_off[i];
+    const uint64_t q0 = A.qname_off[k], q1 = A.qname_off[k + 1], c0 = A.cigar_off[k], c1 = A.cigar_off[k + 1];
+    const uint64_t s0 = A.seq_off[k], s1 = A.seq_off[k + 1], u0 = A.qual_off[k], u1 = A.qual_off[k + 1];
+    if (q1 == q0 && c1 == c0 && s1 == s0 && u1 == u0) return;      // rejected record
+    const uint8_t* p = r + BAM_FIXED;
+    for (uint64_t t = lane; t < q1 - q0; t += 32) A.qname[q0 + t] = p[t];
+    p += (q1 - q0) + 1;                                               // NUL
+    for (uint64_t t = lane; t < c1 - c0; t += 32) A.cigar[c0 + t] = rd32(p + 4 * t);
+    p += 4 * (c1 - c0);
+    for (uint64_t t = lane; t < s1 - s0; t += 32) A.seq[s0 + t] = p[t];
+    p += s1 - s0;
+    for (uint64_t t = lane; t < u1 - u0; t += 32) A.qual[u0 + t] = p[t];
+}
+
+__global__ void __launch_bounds__(256) add_base_u64_kernel(uint64_t n, uint64_t* __restrict__ v, uint64_t base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] += base;
+}
+
+template <class T> int grow(elp_ctx* c, DBuf<T>& b, size_t need, size_t keep) {
+    cudaError_t e = b.reserve(need, c->stream, keep);
+    if (e != cudaSuccess) return c->fail(e == cudaErrorMemoryAllocation ? E_NOMEM : E_CUDA, "device allocation of %zu bytes failed: %s", need * sizeof(T), cudaGetErrorString(e));
+    return E_OK;
+}
+#define TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+}  // namespace
+
+extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_bytes, const uint64_t* record_off, uint64_t n_records) {
+    if (!c || (!records && n_bytes)) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    std::lock_guard<std::mutex> lk(c->append_mu);
+    if (c->sorted) return c->fail(E_STATE, "elp_append_bam after elp_sort_markdup (call elp_reset first)");
+    // record offsets: given, or found by walking the block_size chain
+    std::vector<uint64_t> walked;
+    if (!record_off) {
+        uint64_t x = 0;
+        while (x + 4 <= n_bytes) {
+            walked.push_back(x);
+            const uint32_t bs = (uint32_t)records[x] | ((uint32_t)records[x + 1] << 8) | ((uint32_t)records[x + 2] << 16) | ((uint32_t)records[x + 3] << 24);
+            x += 4ull + bs;
+        }
+        if (x != n_bytes) return c->fail(E_INVAL, "elp_append_bam: the block_size chain does not end at n_bytes");
+        walked.push_back(n_bytes);
+        n_records = walked.size() - 1;
+        record_off = walked.data();
+    }
+    const uint64_t bn = n_records;
+    if (bn == 0) return ELP_OK;
+    if (record_off[bn] != n_bytes) return c->fail(E_INVAL, "elp_append_bam: record_off[n_records] must equal n_bytes");
+    const uint64_t n0 = c->n, n1 = n0 + bn;
+    if (n1 >= (1ull << 32)) return c->fail(E_LIMIT, "more than 2^32-1 reads in one context");
+    cudaStream_t s = c->stream;
+    // @RG ID strings for the RG:Z match
+    if (!c->d_rg_names && c->n_rg) {
+        std::vector<uint8_t> names; std::vector<uint32_t> off(1, 0);
+        for (auto& id : c->rg_ids) { names.insert(names.end(), id.begin(), id.end()); off.push_back((uint32_t)names.size()); }
+        CUDA_TRY(c, cudaMalloc(&c->d_rg_names, std::max<size_t>(names.size(), 1)));
+        CUDA_TRY(c, cudaMalloc(&c->d_rg_name_off, off.size() * 4));
+        CUDA_TRY(c, cudaMemcpy(c->d_rg_names, names.data(), names.size(), cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemcpy(c->d_rg_name_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+    }
+    TRY(grow(c, c->bam_raw, n_bytes + 64, 0)); TRY(grow(c, c->bam_off, bn + 2, 0));
+    TRY(grow(c, c->refid, n1 + 1, n0)); TRY(grow(c, c->pos, n1 + 1, n0)); TRY(grow(c, c->nref, n1 + 1, n0)); TRY(grow(c, c->pnext, n1 + 1, n0)); TRY(grow(c, c->tlen, n1 + 1, n0));
+    TRY(grow(c, c->rg, n1 + 1, n0)); TRY(grow(c, c->flag, n1 + 2, n0)); TRY(grow(c, c->mapq, n1 + 1, n0));
+    TRY(grow(c, c->qname_off, n1 + 2, n0 + 1)); TRY(grow(c, c->cigar_off, n1 + 2, n0 + 1)); TRY(grow(c, c->qual_off, n1 + 2, n0 + 1)); TRY(grow(c, c->seq_off, n1 + 2, n0 + 1));
+    TRY(grow(c, c->scan_tmp, 4 * (bn + 4) + 8, 0));
+    CUDA_TRY(c, cudaMemcpyAsync(c->bam_raw.p, records, n_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->bam_off.p, record_off, (bn + 1) * 8, cudaMemcpyHostToDevice, s));
+    BamArgs A{};
+    A.n = bn; A.n0 = n0; A.raw = c->bam_raw.p; A.rec_off = c->bam_off.p;
+    A.refid = c->refid.p; A.pos = c->pos.p; A.nref = c->nref.p; A.pnext = c->pnext.p; A.tlen = c->tlen.p; A.rg = c->rg.p; A.flag = c->flag.p; A.mapq = c->mapq.p;
+    A.len_qname = c->scan_tmp.p; A.len_cigar = c->scan_tmp.p + (bn + 4); A.len_seq = c->scan_tmp.p + 2 * (bn + 4); A.len_qual = c->scan_tmp.p + 3 * (bn + 4);
+    A.rg_names = c->d_rg_names; A.rg_name_off = c->d_rg_name_off; A.n_rg = c->n_rg; A.n_contigs = c->n_contigs; A.err = c->d_err;
+    c->begin("bam_fixed", (double)bn * 36 + (double)n_bytes * 0.2);
+    bam_fixed_kernel<<<nblk(bn, 256), 256, 0, s>>>(A);
+    c->end(); LAUNCH_CHECK(c);
+    // offsets = arena base + exclusive prefix sums of the lengths
+    const uint64_t bases[4] = {c->n_qname, c->n_cigar, c->n_seq, c->n_qual};
+    uint64_t* outs[4] = {c->qname_off.p + n0, c->cigar_off.p + n0, c->seq_off.p + n0, c->qual_off.p + n0};
+    const uint32_t* lens[4] = {A.len_qname, A.len_cigar, A.len_seq, A.len_qual};
+    uint64_t ends[4];
+    for (int a = 0; a < 4; a++) {
+        TRY(exclusive_scan_u32_to_u64(c, lens[a], outs[a], bn));
+        if (bases[a]) { add_base_u64_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, outs[a], bases[a]); c->launches++; }
+        CUDA_TRY(c, cudaMemcpyAsync(&ends[a], outs[a] + bn, 8, cudaMemcpyDeviceToHost, s));
+    }
+    LAUNCH_CHECK(c);
+    int rc = check_device_errors(c);   // synchronizes
+    if (rc) return rc;
+    TRY(grow(c, c->qname, ends[0] + 64, c->n_qname)); TRY(grow(c, c->cigar, ends[1] + 16, c->n_cigar));
+    TRY(grow(c, c->seq, ends[2] + 64, c->n_seq)); TRY(grow(c, c->qual, ends[3] + 64, c->n_qual));
+    CopyArgs B{};
+    B.n = bn; B.n0 = n0; B.raw = c->bam_raw.p; B.rec_off = c->bam_off.p;
+    B.qname_off = c->qname_off.p; B.cigar_off = c->cigar_off.p; B.seq_off = c->seq_off.p; B.qual_off = c->qual_off.p;
+    B.qname = c->qname.p; B.cigar = c->cigar.p; B.seq = c->seq.p; B.qual = c->qual.p;
+    c->begin("bam_copy", 2.0 * (double)n_bytes);
+    bam_copy_kernel<<<nblk(bn * 32, 256), 256, 0, s>>>(B);
+    c->end(); LAUNCH_CHECK(c);
+    CUDA_TRY(c, cudaStreamSynchronize(s));   // the caller's buffer may be released after return (cgo pointer rules)
+    c->n = n1; c->n_qname = ends[0]; c->n_cigar = ends[1]; c->n_seq = ends[2]; c->n_qual = ends[3];
+    c->adapted = false;
+    return ELP_OK;
+}

@@ -21,6 +21,7 @@
 #define E_REFEND (-14)
 #define E_LIMIT (-15)
 #define E_TILE (-17)
+#define E_BAM (-18)
 #define E_STATE (-16)
 
 // device-side error word bits (one u32 in global memory, OR-ed by kernels, read by the host after the phase)
@@ -34,6 +35,9 @@
 #define DERR_READLEN_LIMIT 0x80u
 #define DERR_TILE 0x100u         // QNAME tile/x/y field that strconv.ParseInt rejects (mark-optical-duplicates.go:57-64)
 #define DERR_TILE_RANGE 0x200u   // tile/x/y outside int32
+#define DERR_BAM 0x400u          // malformed BAM record (lengths / optional fields do not add up)
+#define DERR_BAM_RG 0x800u       // RG:Z value that is not an @RG ID of the header
+#define DERR_BAM_CG 0x1000u      // CG:B long-CIGAR convention
 
 // FLAG bits (sam/sam-types.go:485-520)
 #define F_MULTIPLE 0x1

@@ -94,6 +94,8 @@ struct elp_ctx {
     DBuf<uint64_t> qname_off, cigar_off, qual_off, seq_off;   // [n+1]
     DBuf<uint8_t> qname, seq, qual;
     DBuf<uint32_t> cigar;
+    DBuf<uint8_t> bam_raw; DBuf<uint64_t> bam_off;   // staging of elp_append_bam: raw records and their offsets
+    uint8_t* d_rg_names = nullptr; uint32_t* d_rg_name_off = nullptr; std::vector<std::string> rg_ids;   // @RG IDs for the RG:Z match
     DBuf<int32_t> lseq_stage;       // staging for l_seq of the batch being appended
     DBuf<uint64_t> off_stage;       // staging for batch-relative offsets
 

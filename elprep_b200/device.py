@@ -91,6 +91,12 @@ class Context:
         b.l_seq = _vp(batch.lseq)
         self._ck(self.L.elp_append_batch(self.h, C.byref(b)))
 
+    def append_bam(self, records, record_off=None):
+        """records: uint8 array of consecutive BAM alignment records (each with its block_size); record_off: uint64[n+1] or None"""
+        rec = np.ascontiguousarray(records, dtype=np.uint8)
+        off = np.ascontiguousarray(record_off, dtype=np.uint64) if record_off is not None else None
+        self._ck(self.L.elp_append_bam(self.h, _vp(rec), rec.size, _vp(off), (off.size - 1) if off is not None else 0))
+
     @property
     def n(self):
         return int(self.L.elp_n_reads(self.h))

@@ -35,6 +35,7 @@ extern "C" {
 #define ELP_ELIMIT (-15)     /* an implementation limit was exceeded (text says which) */
 #define ELP_ESTATE (-16)     /* entry point called in the wrong phase order */
 #define ELP_ETILE (-17)      /* a QNAME tile/x/y field that strconv.ParseInt rejects (filters/mark-optical-duplicates.go:57-64) */
+#define ELP_EBAM (-18)       /* malformed BAM alignment record, or an RG:Z value that is not an @RG ID */
 
 /* sam.SortingOrder (sam/sam-types.go:40-58) */
 #define ELP_SO_KEEP 0
@@ -105,6 +106,14 @@ int elp_set_known_sites(elp_ctx *ctx, int32_t contig, const int32_t *start_end_p
 
 /* ---- phase 1: (*sam.Sam).AddNodes receiving batches (sam/filter-pipeline.go:108-128) ---- */
 int elp_append_batch(elp_ctx *ctx, const elp_batch *batch);
+/* The same, straight from decompressed BAM alignment records: what parseBamAlignment reads on the host
+ * (sam/bam-files.go:314-400) is parsed on the device instead, so a Go caller hands over the bytes of a BGZF block without
+ * building []*sam.Alignment first.  records: n_bytes of consecutive records, each starting with its 4-byte block_size;
+ * record_off[n_records + 1]: byte offset of every record (record_off[n_records] == n_bytes), or NULL to let the library
+ * walk the block_size chain.  refID / next_refID index @SQ directly (they ARE the REFID temps); POS and PNEXT become
+ * 1-based; the RG:Z tag is matched against elp_config.rg_id (an unknown value is ELP_EBAM, no RG tag is rg = -1).
+ * Not supported: the CG:B long-CIGAR convention (ELP_ELIMIT).  Thread-safe like elp_append_batch. */
+int elp_append_bam(elp_ctx *ctx, const uint8_t *records, uint64_t n_bytes, const uint64_t *record_off, uint64_t n_records);
 uint64_t elp_n_reads(const elp_ctx *ctx);
 
 /* filters.MarkDuplicates (filters/mark-duplicates.go:406-445) + By(CoordinateLess).ParallelStableSort in the

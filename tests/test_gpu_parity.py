@@ -363,3 +363,57 @@ def test_two_workers_spread_pairs_on_device():
         assert [g[k] for k in _lib.ElpDupMetrics.COUNTERS] == [wm.counters[slot][k] for k in oracle.COUNTERS], slot
         assert g["hist"] == wm.hist[slot] and g["estimated_library_size"] == wm.library_size[slot]
     ctx.close()
+
+
+# ---- BAM records parsed on the device (sam/bam-files.go:314-400) ----
+def test_bam_ingest_equals_column_ingest():
+    """elp_append_bam over encoded records gives the same sorted order, FLAGs, BQSR tables and QUAL bytes as elp_append_batch
+    over the columns -- and both equal the oracle"""
+    from elprep_b200 import device
+    from util import encode_bam
+    w = synth.make_workload(6_000, SMALL, seed=17, unmapped_frac=0.05)
+    o = oracle_pipeline(w)
+    raw, offs = encode_bam(w.batch, w.header)
+    nrec = offs.size - 1
+    cuts = [0, nrec // 3, nrec // 2, nrec]                      # three calls; the last one lets the library walk the block_size chain
+    ctx = device.Context(w.header)
+    for ci in range(len(w.header.SQ)):
+        ctx.set_reference(ci, w.contig_bases[ci]); ctx.set_known_sites(ci, w.sites[ci], already_flat=True)
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        part = raw[int(offs[a]):int(offs[b])]
+        ctx.append_bam(part, (offs[a:b + 1] - offs[a]) if b != nrec else None)
+    assert ctx.n == w.batch.n
+    ctx.sort_markdup()
+    ctx.bqsr_gather(); ctx.bqsr_finalize(None); ctx.bqsr_apply()
+    idx, flag, qoff, qual = ctx.fetch()
+    assert np.array_equal(idx, o["perm"]) and np.array_equal(flag, o["flag"])
+    assert np.array_equal(qoff, o["qual_off"]) and np.array_equal(qual[:int(qoff[-1])], o["qual"])
+    d, _ = oracle_tables_dense(o["tables"], 500)
+    assert np.array_equal(ctx.tables_get(), d)
+    ctx.close()
+
+
+def test_bam_ingest_errors():
+    from elprep_b200 import device
+    from util import encode_bam
+    w = synth.make_workload(300, SMALL, seed=18, want_reference=False)
+    raw, offs = encode_bam(w.batch, w.header, with_aux=False)
+    # an RG:Z value the header does not know (the reference would invent a table entry; here it is an error)
+    h2 = sam.Header(sq=w.header.SQ, rg=[{"ID": "other"}])
+    ctx = device.Context(h2)
+    with pytest.raises(device.ElprepError) as ei:
+        ctx.append_bam(raw, offs)
+    assert ei.value.code == -18 and "RG:Z" in str(ei.value) and ctx.n == 0
+    ctx.close()
+    # a record whose lengths do not add up; nothing is appended
+    bad = raw.copy(); bad[int(offs[5]) + 20] ^= 0x40                  # l_seq of record 5
+    ctx = device.Context(w.header)
+    with pytest.raises(device.ElprepError) as ei:
+        ctx.append_bam(bad, offs)
+    assert ei.value.code == -18 and ctx.n == 0
+    ctx.append_bam(raw, offs)                                          # the context is still usable
+    assert ctx.n == w.batch.n
+    # block_size chain that does not end at n_bytes
+    with pytest.raises(device.ElprepError):
+        ctx.append_bam(raw[:-3], None)
+    ctx.close()

@@ -78,3 +78,71 @@ def gpu_pipeline(w, bqsr=True, n_batches=1, max_cycle=500, quantize_levels=0, sq
     finally:
         if not keep_ctx:
             ctx.close()
+
+
+# ---- BAM alignment records (sam/bam-files.go:300-400) for the device ingest tests ----
+def encode_bam(batch, header, rng=None, with_aux=True):
+    """AlignmentBatch -> (uint8 record bytes, uint64 record offsets [n+1]).  Each record carries its block_size, the fixed
+    fields of parseBamAlignment, NUL-terminated name, CIGAR words, SEQ nibbles, QUAL bytes and typed optional fields
+    (RG:Z plus a mix of the other value types, so that the tag walk is exercised)."""
+    import struct
+    rng = rng or np.random.default_rng(0)
+    ids = [r["ID"] for r in header.RG]
+    out, offs = bytearray(), [0]
+    qo, co = batch.qname_off.astype(np.int64), batch.cigar_off.astype(np.int64)
+    so, uo = batch.seq_off.astype(np.int64), batch.qual_off.astype(np.int64)
+    for i in range(batch.n):
+        name = bytes(batch.qname[qo[i]:qo[i + 1]]) + b"\0"
+        cig = batch.cigar[co[i]:co[i + 1]].astype("<u4").tobytes()
+        L = int(batch.lseq[i])
+        seq = bytes(batch.seq[so[i]:so[i] + (L + 1) // 2]); qual = bytes(batch.qual[uo[i]:uo[i] + L])
+        aux = b""
+        if with_aux:
+            k = int(rng.integers(0, 4))
+            if k >= 1: aux += b"NMC" + struct.pack("<B", int(rng.integers(0, 9)))
+            if k >= 2: aux += b"MDZ" + b"75A74\0"
+            if int(batch.rg[i]) >= 0: aux += b"RGZ" + ids[int(batch.rg[i])].encode() + b"\0"
+            if k >= 3: aux += b"ASi" + struct.pack("<i", -5) + b"XSf" + struct.pack("<f", 1.5) + b"ZBBs" + struct.pack("<I", 3) + struct.pack("<3h", 1, -2, 3) + b"XAA" + b"q"
+        elif int(batch.rg[i]) >= 0:
+            aux += b"RGZ" + ids[int(batch.rg[i])].encode() + b"\0"
+        body = struct.pack("<iiBBHHHiiii", int(batch.refid[i]), int(batch.pos[i]) - 1, len(name), int(batch.mapq[i]), 4680, (co[i + 1] - co[i]) & 0xffff,
+                           int(batch.flag[i]), L, int(batch.nref[i]), int(batch.pnext[i]) - 1, int(batch.tlen[i])) + name + cig + seq + qual + aux
+        out += struct.pack("<I", len(body)) + body
+        offs.append(len(out))
+    return np.frombuffer(bytes(out), dtype=np.uint8).copy(), np.array(offs, dtype=np.uint64)
+
+
+def decode_bam(raw, offs, header):
+    """restatement of parseBamAlignment (sam/bam-files.go:314-400) for the fields of the path -> AlignmentBatch"""
+    import struct
+    from elprep_b200 import sam
+    ids = {r["ID"]: k for k, r in enumerate(header.RG)}
+    cols = {k: [] for k in ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "lseq")}
+    qn, cg, sq, ql, qoff, coff = bytearray(), [], bytearray(), bytearray(), [0], [0]
+    b = raw.tobytes()
+    sizes = {"A": 1, "c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}
+    for i in range(len(offs) - 1):
+        r = b[int(offs[i]):int(offs[i + 1])]
+        bs, refid, pos, lname, mapq, _bin, ncig, flag, lseq, nref, pnext, tlen = struct.unpack_from("<IiiBBHHHiiii", r, 0)
+        assert bs + 4 == len(r)
+        x = 36
+        qn += r[x:x + lname - 1]; qoff.append(len(qn)); x += lname
+        cg += list(struct.unpack_from("<%dI" % ncig, r, x)); coff.append(len(cg)); x += 4 * ncig
+        sq += r[x:x + (lseq + 1) // 2]; x += (lseq + 1) // 2
+        ql += r[x:x + lseq]; x += lseq
+        rg = -1
+        while x < len(r):
+            tag, ty = r[x:x + 2], chr(r[x + 2]); x += 3
+            if ty in sizes: x += sizes[ty]
+            elif ty in "ZH":
+                e = r.index(b"\0", x)
+                if tag == b"RG" and ty == "Z": rg = ids[r[x:e].decode()]
+                x = e + 1
+            elif ty == "B":
+                sub, cnt = chr(r[x]), struct.unpack_from("<I", r, x + 1)[0]; x += 5 + cnt * sizes[sub]
+            else: raise ValueError("bad type")
+        for k, v in zip(cols, (refid, pos + 1, flag, mapq, nref, pnext + 1, tlen, rg, lseq)):
+            cols[k].append(v)
+    return sam.AlignmentBatch(qname_off=np.array(qoff, np.uint64), qname=np.frombuffer(bytes(qn), np.uint8), cigar_off=np.array(coff, np.uint64),
+                              cigar=np.array(cg, np.uint32), seq=np.frombuffer(bytes(sq), np.uint8), qual=np.frombuffer(bytes(ql), np.uint8).copy(),
+                              **{k: np.array(v) for k, v in cols.items()})

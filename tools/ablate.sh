@@ -4,7 +4,7 @@ set -e
 cd "$(dirname "$0")/../elprep_b200/csrc"
 mkdir -p ../lib/exp
 rm -f ../lib/exp/*.so
-SRCS="api.cu sort.cu markdup.cu optical.cu coordsort.cu bqsr_gather.cu bqsr_apply.cu bqsr_finalize.cu"
+SRCS="api.cu bam_ingest.cu sort.cu markdup.cu optical.cu coordsort.cu bqsr_gather.cu bqsr_apply.cu bqsr_finalize.cu"
 FL="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-ffp-contract=off -shared"
 for spec in "$@"; do
   name="${spec%%:*}"; defs="${spec#*:}"; [ "$defs" = "$spec" ] && defs=""
