@@ -8,7 +8,9 @@
 //                     the typed optional fields (sam/bam-files.go optionalBAMFieldParseTable) and matched against @RG IDs
 //   bam_copy_kernel   one warp per record: QNAME bytes (without the NUL), CIGAR words (already `len<<4|op`), SEQ nibbles
 //                     and QUAL bytes (phred without +33) are byte-for-byte the device layout -> four segmented copies
-// Offsets come from device prefix sums of the lengths.  Not handled (error return): the CG:B long-CIGAR convention (:376-392),
+// Offsets come from device prefix sums of the lengths.  The raw records stay in a device arena so that the write phase can
+// hand them back (elp_fetch_bam): output order, FLAG and QUAL patched, everything else -- names, CIGAR, tags -- untouched
+// (the counterpart of formatting every *sam.Alignment again, sam/bam-files.go:635-735).  Not handled (error return): the CG:B long-CIGAR convention (:376-392),
 // an RG:Z value that is not an @RG ID of the header.
 #include "ctx.h"
 #include "../../include/elprep_b200.h"
@@ -130,6 +132,36 @@ __global__ void __launch_bounds__(256) add_base_u64_kernel(uint64_t n, uint64_t*
     if (i < n) v[i] += base;
 }
 
+// ---- egress ----
+__global__ void __launch_bounds__(256) bam_out_len_kernel(uint64_t n, const uint32_t* __restrict__ perm, const uint64_t* __restrict__ all_off, uint32_t* __restrict__ len) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) { const uint32_t i = perm[k]; len[k] = (uint32_t)(all_off[i + 1] - all_off[i]); }
+}
+// one warp per output record: copy the stored record, patch FLAG (bytes 18..19 of the record with its block_size) and QUAL
+__global__ void __launch_bounds__(256) bam_out_copy_kernel(uint64_t n, uint64_t first, const uint32_t* __restrict__ perm, const uint64_t* __restrict__ all_off,
+                                                            const uint8_t* __restrict__ all, const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out,
+                                                            const uint16_t* __restrict__ s_flag, const uint64_t* __restrict__ s_out_off, const uint8_t* __restrict__ qual_out) {
+    const unsigned lane = threadIdx.x & 31;
+    const uint64_t kk = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (kk >= n) return;
+    const uint64_t k = first + kk;
+    const uint32_t i = perm[k];
+    const uint8_t* r = all + all_off[i];
+    const uint64_t len = all_off[i + 1] - all_off[i];
+    uint8_t* o = out + out_off[kk];
+    const uint32_t l_name = r[12], n_cig = rd16(r + 16);
+    const int32_t l_seq = (int32_t)rd32(r + 20);
+    const uint64_t q0 = BAM_FIXED + (uint64_t)l_name + 4ull * n_cig + (uint64_t)((l_seq + 1) >> 1), q1 = q0 + (uint64_t)l_seq;
+    const uint16_t f = s_flag[k];
+    const uint8_t* nq = qual_out ? qual_out + s_out_off[k] : nullptr;
+    for (uint64_t t = lane; t < len; t += 32) {
+        uint8_t v = r[t];
+        if (t == 18) v = (uint8_t)(f & 0xff); else if (t == 19) v = (uint8_t)(f >> 8);
+        else if (nq && t >= q0 && t < q1) v = nq[t - q0];
+        o[t] = v;
+    }
+}
+
 template <class T> int grow(elp_ctx* c, DBuf<T>& b, size_t need, size_t keep) {
     cudaError_t e = b.reserve(need, c->stream, keep);
     if (e != cudaSuccess) return c->fail(e == cudaErrorMemoryAllocation ? E_NOMEM : E_CUDA, "device allocation of %zu bytes failed: %s", need * sizeof(T), cudaGetErrorString(e));
@@ -211,7 +243,55 @@ extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_byt
     bam_copy_kernel<<<nblk(bn * 32, 256), 256, 0, s>>>(B);
     c->end(); LAUNCH_CHECK(c);
     CUDA_TRY(c, cudaStreamSynchronize(s));   // the caller's buffer may be released after return (cgo pointer rules)
+    // keep the raw records for elp_fetch_bam (only meaningful while every read of the context came in as BAM)
+    if (c->bam_reads == n0) {
+        TRY(grow(c, c->bam_all, c->n_bam + n_bytes + 64, c->n_bam)); TRY(grow(c, c->bam_all_off, n1 + 2, n0 + 1));
+        CUDA_TRY(c, cudaMemcpyAsync(c->bam_all.p + c->n_bam, c->bam_raw.p, n_bytes, cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(c, cudaMemcpyAsync(c->bam_all_off.p + n0, c->bam_off.p, (bn + 1) * 8, cudaMemcpyDeviceToDevice, s));
+        if (c->n_bam) { add_base_u64_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->bam_all_off.p + n0, c->n_bam); c->launches++; }
+        CUDA_TRY(c, cudaStreamSynchronize(s));
+        c->n_bam += n_bytes; c->bam_reads = n1;
+    }
     c->n = n1; c->n_qname = ends[0]; c->n_cigar = ends[1]; c->n_seq = ends[2]; c->n_qual = ends[3];
     c->adapted = false;
+    return ELP_OK;
+}
+
+static int bam_out_prepare(elp_ctx* c, uint64_t first, uint64_t n, uint64_t* total) {
+    if (!c->sorted) return c->fail(E_STATE, "elp_fetch_bam before elp_sort_markdup");
+    if (c->bam_reads != c->n) return c->fail(E_STATE, "elp_fetch_bam: not every read of this context came in through elp_append_bam");
+    if (first + n > c->n) return c->fail(E_INVAL, "elp_fetch_bam: range [%llu,%llu) exceeds %llu reads", (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)c->n);
+    TRY(grow(c, c->scan_tmp, n + 8, 0)); TRY(grow(c, c->off_stage, n + 2, 0));
+    bam_out_len_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->perm.p + first, c->bam_all_off.p, c->scan_tmp.p); c->launches++;
+    LAUNCH_CHECK(c);
+    TRY(exclusive_scan_u32_to_u64(c, c->scan_tmp.p, c->off_stage.p, n));
+    CUDA_TRY(c, cudaMemcpyAsync(total, c->off_stage.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return E_OK;
+}
+
+extern "C" uint64_t elp_fetch_bam_bytes(elp_ctx* c, uint64_t first, uint64_t n) {
+    if (!c || n == 0) return 0;
+    cudaSetDevice(c->device);
+    uint64_t total = 0;
+    if (bam_out_prepare(c, first, n, &total)) return 0;
+    return total;
+}
+
+extern "C" int elp_fetch_bam(elp_ctx* c, uint64_t first, uint64_t n, uint8_t* out, uint64_t capacity, uint64_t* record_off) {
+    if (!c || (!out && n)) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (n == 0) { if (record_off) record_off[0] = 0; return ELP_OK; }
+    uint64_t total = 0;
+    TRY(bam_out_prepare(c, first, n, &total));
+    if (total > capacity) return c->fail(E_INVAL, "elp_fetch_bam: output buffer too small (%llu > %llu)", (unsigned long long)total, (unsigned long long)capacity);
+    TRY(grow(c, c->bam_raw, total + 64, 0));      // staging for the formatted records
+    c->begin("bam_format", 2.0 * (double)total);
+    bam_out_copy_kernel<<<nblk(n * 32, 256), 256, 0, c->stream>>>(n, first, c->perm.p, c->bam_all_off.p, c->bam_all.p, c->off_stage.p, c->bam_raw.p, c->s_flag.p, c->s_out_off.p,
+                                                                  c->qual_out_valid ? c->qual_out.p : nullptr);
+    c->end(); LAUNCH_CHECK(c);
+    CUDA_TRY(c, cudaMemcpyAsync(out, c->bam_raw.p, total, cudaMemcpyDeviceToHost, c->stream));
+    if (record_off) CUDA_TRY(c, cudaMemcpyAsync(record_off, c->off_stage.p, (n + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ELP_OK;
 }

@@ -191,6 +191,14 @@ class Context:
         self._ck(self.L.elp_fetch(self.h, first, n, _vp(idx), _vp(flag), _vp(qoff), _vp(qual) if want_qual else None, qual.size))
         return idx, flag, qoff, qual
 
+    def fetch_bam(self, first=0, n=None):
+        """-> (uint8 record bytes, uint64 record offsets [n+1]) of output records [first, first+n), FLAG and QUAL patched"""
+        n = self.n - first if n is None else n
+        nb = int(self.L.elp_fetch_bam_bytes(self.h, first, n))
+        out, off = np.empty(max(nb, 1), np.uint8), np.empty(n + 1, np.uint64)
+        self._ck(self.L.elp_fetch_bam(self.h, first, n, _vp(out), out.size, _vp(off)))
+        return out[:nb], off
+
     def debug_adapt(self):
         u, s = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
         self._ck(self.L.elp_debug_adapt(self.h, _vp(u), _vp(s)))

@@ -179,6 +179,12 @@ int elp_bqsr_apply(elp_ctx *ctx);
 int elp_fetch(elp_ctx *ctx, uint64_t first, uint64_t n, uint64_t *record_index, uint16_t *flag, uint64_t *qual_off, uint8_t *qual, uint64_t qual_capacity);
 uint64_t elp_fetch_qual_bytes(elp_ctx *ctx, uint64_t first, uint64_t n);
 /* per-read temps of adaptAlignment (filters/mark-duplicates.go:153-156), arrival order; for parity tests */
+/* The same as BAM alignment records (only if every read came in through elp_append_bam): output records [first, first+n) are
+ * the stored records with FLAG and -- once elp_bqsr_apply has run -- QUAL replaced; names, CIGAR and optional fields are the
+ * input bytes.  This stands in for formatting every *sam.Alignment again (sam/bam-files.go:635-735); the caller BGZF-
+ * compresses the result.  record_off[n+1] may be NULL. */
+uint64_t elp_fetch_bam_bytes(elp_ctx *ctx, uint64_t first, uint64_t n);
+int elp_fetch_bam(elp_ctx *ctx, uint64_t first, uint64_t n, uint8_t *out, uint64_t capacity, uint64_t *record_off);
 int elp_debug_adapt(elp_ctx *ctx, int32_t *upos, int32_t *score);
 
 /* ---- measurement ---- */

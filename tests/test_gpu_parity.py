@@ -390,6 +390,21 @@ def test_bam_ingest_equals_column_ingest():
     assert np.array_equal(qoff, o["qual_off"]) and np.array_equal(qual[:int(qoff[-1])], o["qual"])
     d, _ = oracle_tables_dense(o["tables"], 500)
     assert np.array_equal(ctx.tables_get(), d)
+    # egress: the stored records in output order with FLAG and QUAL patched, everything else byte-identical
+    from util import decode_bam
+    out, ooff = ctx.fetch_bam()
+    b2 = decode_bam(out, ooff, w.header)
+    srt = w.batch.take(o["perm"].astype(np.int64))
+    assert np.array_equal(b2.flag, o["flag"]) and np.array_equal(b2.qual, o["qual"])
+    for f in ("refid", "pos", "mapq", "nref", "pnext", "tlen", "rg", "qname", "qname_off", "cigar", "cigar_off", "lseq", "seq"):
+        assert np.array_equal(getattr(b2, f), getattr(srt, f)), f
+    for k in (0, 1, 77, int(ooff.size) - 2):                              # optional fields untouched
+        i = int(o["perm"][k]); L = int(w.batch.lseq[i])
+        rin, rout = raw[int(offs[i]):int(offs[i + 1])], out[int(ooff[k]):int(ooff[k + 1])]
+        tail = 36 + int(rin[12]) + 4 * int(rin[16] | (rin[17] << 8)) + (L + 1) // 2 + L
+        assert rin.size == rout.size and np.array_equal(rin[tail:], rout[tail:]) and np.array_equal(rin[:18], rout[:18])
+    part, poff = ctx.fetch_bam(100, 50)                                    # a sub-range
+    assert np.array_equal(part, out[int(ooff[100]):int(ooff[150])]) and np.array_equal(poff, ooff[100:151] - ooff[100])
     ctx.close()
 
 
