@@ -104,3 +104,22 @@ def make_workload(n_pairs, contigs, seed=20260924, L=150, dup_frac=0.10, optical
             k = lib.synth_known_sites(C.c_uint64(seed), C.c_int32(ci), C.c_int32(ln), vp(se), C.c_int64(cap))
             sites.append(se[:2 * k].reshape(-1, 2).copy())
     return Workload(header, batch, bases, sites, dict(n_pairs=n_pairs, seed=seed, L=L, contigs=contigs))
+
+
+def encode_bam(batch, header, threads=8):
+    """columns -> (uint8 BAM alignment records, uint64 record offsets [n+1]); test / bench infrastructure for elp_append_bam"""
+    L = _L()
+    ids = [r["ID"].encode() for r in header.RG]
+    rg_ids = np.frombuffer(b"".join(ids) or b"\0", dtype=np.uint8).copy()
+    rg_off = np.zeros(len(ids) + 1, dtype=np.uint32)
+    if ids:
+        rg_off[1:] = np.cumsum([len(x) for x in ids])
+    n = batch.n
+    rec_off = np.zeros(n + 1, dtype=np.uint64)
+    cols = [batch.refid, batch.pos, batch.flag, batch.mapq, batch.nref, batch.pnext, batch.tlen, batch.rg, batch.qname_off, batch.qname, batch.cigar_off,
+            batch.cigar, batch.lseq, batch.seq_off, batch.seq, batch.qual_off, batch.qual, rg_ids, rg_off]
+    ptr = [a.ctypes.data_as(C.c_void_p) for a in cols]
+    L.synth_encode_bam(C.c_int64(n), *ptr, rec_off.ctypes.data_as(C.c_void_p), None, C.c_int32(threads))
+    out = np.empty(int(rec_off[-1]), dtype=np.uint8)
+    L.synth_encode_bam(C.c_int64(n), *ptr, rec_off.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_int32(threads))
+    return out, rec_off

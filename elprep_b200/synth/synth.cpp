@@ -308,4 +308,38 @@ int64_t synth_known_sites(uint64_t seed, int32_t contig, int32_t contig_len, int
     }
     return n;
 }
+
+// columns -> BAM alignment records (sam/bam-files.go:300-400 layout; each with its block_size, RG:Z and an NM:C tag).
+// pass 1 (out == nullptr): fills rec_off[n+1]; pass 2: writes the bytes.  rg_ids: concatenated @RG ID strings, rg_id_off[n_rg+1].
+int synth_encode_bam(int64_t n, const int32_t* refid, const int32_t* pos, const uint16_t* flag, const uint8_t* mapq, const int32_t* nref, const int32_t* pnext,
+                     const int32_t* tlen, const int32_t* rg, const uint64_t* qname_off, const uint8_t* qname, const uint64_t* cigar_off, const uint32_t* cigar,
+                     const int32_t* lseq, const uint64_t* seq_off, const uint8_t* seq, const uint64_t* qual_off, const uint8_t* qual,
+                     const uint8_t* rg_ids, const uint32_t* rg_id_off, uint64_t* rec_off, uint8_t* out, int32_t threads) {
+    auto rec_len = [&](int64_t i) -> uint64_t {
+        const uint64_t qn = qname_off[i + 1] - qname_off[i], nc = cigar_off[i + 1] - cigar_off[i], L = (uint64_t)lseq[i];
+        uint64_t aux = 4;   // NM:C
+        if (rg[i] >= 0) aux += 3 + (rg_id_off[rg[i] + 1] - rg_id_off[rg[i]]) + 1;
+        return 36 + qn + 1 + 4 * nc + (L + 1) / 2 + L + aux;
+    };
+    if (!out) { rec_off[0] = 0; for (int64_t i = 0; i < n; i++) rec_off[i + 1] = rec_off[i] + rec_len(i); return 0; }
+    par_for(n, threads, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t i = lo; i < hi; i++) {
+            uint8_t* r = out + rec_off[i];
+            const uint64_t len = rec_off[i + 1] - rec_off[i];
+            const uint32_t qn = (uint32_t)(qname_off[i + 1] - qname_off[i]), nc = (uint32_t)(cigar_off[i + 1] - cigar_off[i]); const int32_t L = lseq[i];
+            auto w32 = [&](int o, uint32_t v) { r[o] = v & 255; r[o + 1] = (v >> 8) & 255; r[o + 2] = (v >> 16) & 255; r[o + 3] = v >> 24; };
+            w32(0, (uint32_t)(len - 4)); w32(4, (uint32_t)refid[i]); w32(8, (uint32_t)(pos[i] - 1));
+            r[12] = (uint8_t)(qn + 1); r[13] = mapq[i]; r[14] = 0x48; r[15] = 0x12; r[16] = nc & 255; r[17] = (nc >> 8) & 255; r[18] = flag[i] & 255; r[19] = flag[i] >> 8;
+            w32(20, (uint32_t)L); w32(24, (uint32_t)nref[i]); w32(28, (uint32_t)(pnext[i] - 1)); w32(32, (uint32_t)tlen[i]);
+            uint8_t* p = r + 36;
+            std::memcpy(p, qname + qname_off[i], qn); p += qn; *p++ = 0;
+            std::memcpy(p, cigar + cigar_off[i], 4ull * nc); p += 4ull * nc;
+            std::memcpy(p, seq + seq_off[i], (size_t)(L + 1) / 2); p += (L + 1) / 2;
+            std::memcpy(p, qual + qual_off[i], (size_t)L); p += L;
+            *p++ = 'N'; *p++ = 'M'; *p++ = 'C'; *p++ = (uint8_t)(i & 7);
+            if (rg[i] >= 0) { *p++ = 'R'; *p++ = 'G'; *p++ = 'Z'; const uint32_t a = rg_id_off[rg[i]], b = rg_id_off[rg[i] + 1]; std::memcpy(p, rg_ids + a, b - a); p += b - a; *p++ = 0; }
+        }
+    });
+    return 0;
+}
 }
