@@ -193,6 +193,7 @@ extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_byt
     const uint64_t bn = n_records;
     if (bn == 0) return ELP_OK;
     if (record_off[bn] != n_bytes) return c->fail(E_INVAL, "elp_append_bam: record_off[n_records] must equal n_bytes");
+    for (uint64_t i = 0; i < bn; i++) if (record_off[i + 1] < record_off[i] || record_off[i + 1] > n_bytes) return c->fail(E_INVAL, "elp_append_bam: record_off must be non-decreasing and within n_bytes");
     const uint64_t n0 = c->n, n1 = n0 + bn;
     if (n1 >= (1ull << 32)) return c->fail(E_LIMIT, "more than 2^32-1 reads in one context");
     cudaStream_t s = c->stream;

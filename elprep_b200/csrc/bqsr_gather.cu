@@ -43,11 +43,6 @@ struct Clip {          // working copy of one alignment (lane 0 only)
 
 __device__ int32_t aln_end(const Clip& a) { int32_t l = 0; for (int i = 0; i < a.nc; i++) l += cons_ref(op_of(a.cg[i])) * len_of(a.cg[i]); return a.pos + l - 1; }
 __device__ int soft_start(const Clip& a) { int32_t s = a.pos; for (int i = 0; i < a.nc; i++) { int o = op_of(a.cg[i]); if (o == 4) s -= len_of(a.cg[i]); else if (o != 5) break; } return s; }
-__device__ int soft_end(const Clip& a) {
-    int32_t end = aln_end(a), se = end;
-    for (int i = a.nc - 1; i >= 0; i--) { int o = op_of(a.cg[i]); if (o == 4) se += len_of(a.cg[i]); else if (o != 5) return se; }
-    return end;
-}
 __device__ int read_len(const uint32_t* cg, int nc) { int l = 0; for (int i = 0; i < nc; i++) l += cons_read(op_of(cg[i])) * len_of(cg[i]); return l; }
 
 // computeReadCoordinateForReferenceCoordinate, filters/utils.go:267-326

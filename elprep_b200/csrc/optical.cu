@@ -23,7 +23,6 @@
 
 namespace {
 
-constexpr uint32_t NONE32 = 0xffffffffu;
 constexpr int LIST_CAP = 300000;        // :291-299, :330
 constexpr int SMALL_MAX = 32;
 
