@@ -99,7 +99,11 @@ struct ReadShape { int32_t pos; uint32_t cig[4]; int ncig; };
 // kind: 0 = all M, 1 = soft clip (left or right), 2 = insertion, 3 = deletion, 4 = soft clip + indel
 void make_shape(Rng& r, int L, int32_t anchor, bool anchor_is_end, ReadShape& s) {
     double u = r.uni();
-    int k = 1 + (int)r.below(40), il = 1 + (int)r.below(5), ip = 20 + (int)r.below((uint32_t)(L - 80));
+    // clip / indel geometry; the L >= 100 formulas are the original ones (same random stream), shorter reads scale them down
+    const int kmax = L >= 100 ? 40 : std::max(1, L / 4);
+    int k = 1 + (int)r.below((uint32_t)kmax), il = 1 + (int)r.below(5), ip;
+    if (L - 80 > 0 && L >= 100) ip = 20 + (int)r.below((uint32_t)(L - 80));
+    else { const int lo = std::max(2, L / 5); ip = lo + (int)r.below((uint32_t)std::max(1, L - 2 * lo - 8 - kmax)); }
     bool left = (r.next() & 1) != 0;
     auto M = [](int n) { return ((uint32_t)n << 4) | 0u; };
     auto I = [](int n) { return ((uint32_t)n << 4) | 1u; };

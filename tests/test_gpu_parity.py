@@ -85,6 +85,27 @@ def test_full_path_small(seed, kw):
     assert int(((g["flag"] & 0x400) != 0).sum()) > 0 or kw.get("unmapped_frac", 0) > 0.2
 
 
+@pytest.mark.parametrize("L", [36, 75, 100, 151, 250, 300])
+def test_read_lengths(L):
+    """other read lengths: the BQSR chunk kernels give every read ceil(L/16) lanes, so 36 / 75 / 100 / 151 / 250 / 300 bases mean
+    10 / 6 / 4 / 3 / 2 / 1 reads per warp step (and a partial last chunk of every size)"""
+    w = synth.make_workload(4_000, SMALL, seed=100 + L, L=L)
+    assert int(w.batch.lseq.max()) == L
+    g = gpu_pipeline(w, n_batches=2)
+    o = oracle_pipeline(w)
+    _compare(w, g, o)
+
+
+def test_mixed_read_lengths():
+    """reads of different lengths in one context (lanes per read follow the longest)"""
+    a = synth.make_workload(2_000, SMALL, seed=201, L=150)
+    b = synth.make_workload(2_000, SMALL, seed=202, L=49)
+    w = synth.Workload(a.header, sam.AlignmentBatch.concat([a.batch, b.batch]), a.contig_bases, a.sites, a.params)
+    g = gpu_pipeline(w, n_batches=3)
+    o = oracle_pipeline(w)
+    _compare(w, g, o)
+
+
 def test_full_path_c1_shape():
     """config[0] shape (single contig), 200k reads: sort + markdup + BQSR"""
     w = synth.make_workload(100_000, [("chr20", 6_444_416)], seed=20260924)
