@@ -76,6 +76,16 @@ __global__ void __launch_bounds__(256) adapt_kernel(uint64_t n, const uint16_t* 
                 const uint4 v = ld_stream_u4(qual + a);
                 const int lo = (int)(q0 > a ? q0 - a : 0), hi = (int)((q1 < a + 16 ? q1 : a + 16) - a);
                 const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                if (lo == 0 && hi == 16) {          // interior chunk: no byte masks
+#pragma unroll
+                    for (int t = 0; t < 4; t++) {
+                        const uint32_t x = w[t] & 0x7f7f7f7fu;
+                        bad |= (x + 0x22222222u) & 0x80808080u;
+                        const uint32_t ge15 = ((x + 0x71717171u) & 0x80808080u) >> 7;
+                        s = __dp4a(x & (ge15 * 0xffu), 0x01010101u, s);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int t = 0; t < 4; t++) {
                     int wlo = lo - 4 * t, whi = hi - 4 * t;
