@@ -453,3 +453,26 @@ def test_bam_ingest_errors():
     with pytest.raises(device.ElprepError):
         ctx.append_bam(raw[:-3], None)
     ctx.close()
+
+
+def test_against_committed_golden_digests(tmp_path):
+    """the CUDA path against tests/golden/oracle_regression.json (digests committed by tools/make_golden.py)"""
+    import hashlib, json, os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import make_golden
+    from elprep_b200 import device, _lib
+    gold = json.load(open(os.path.join(root, "tests", "golden", "oracle_regression.json")))
+    for name, case in make_golden.CASES.items():
+        w = synth.make_workload(case["n_pairs"], case["contigs"], **case["kw"])
+        g = gpu_pipeline(w, n_batches=2)
+        exp = gold[name]
+        assert make_golden.digest(g["perm"]) == exp["perm"] and make_golden.digest(g["flag"]) == exp["flag"], name
+        assert make_golden.digest(g["qual"]) == exp["qual"] and hashlib.sha256(g["report"].encode()).hexdigest()[:24] == exp["report"], name
+        ctx = device.Context(w.header)
+        ctx.append(w.batch)
+        ctx.sort_markdup(device.SO_KEEP, _lib.MARKDUP_OPTICAL)
+        p = str(tmp_path / (name + ".txt"))
+        ctx.print_duplicates_metrics(p, "elprep filter in out", "T")
+        assert hashlib.sha256(open(p).read().encode()).hexdigest()[:24] == exp["metrics"], name
+        ctx.close()
