@@ -43,7 +43,8 @@ EXPORTS = ["elp_create", "elp_destroy", "elp_last_error", "elp_reserve", "elp_re
            "elp_bqsr_empirical_get", "elp_bqsr_apply", "elp_fetch", "elp_fetch_qual_bytes", "elp_fetch_bam", "elp_fetch_bam_bytes", "elp_debug_adapt", "elp_launch_count",
            "elp_kernel_stats", "elp_synchronize", "elp_reset_stats", "elp_timer_start", "elp_timer_stop", "elp_debug_sort_u64", "elp_debug_sort_u128",
            "elp_optical_n_libraries", "elp_optical_library_name", "elp_optical_metrics", "elp_optical_histogram", "elp_optical_merge",
-           "elp_print_duplicates_metrics"]
+           "elp_print_duplicates_metrics",
+           "elp_bgzf_inflate_bound", "elp_bgzf_inflate", "elp_bgzf_deflate_bound", "elp_bgzf_deflate", "elp_bam_header_size"]
 
 _lib = None
 
@@ -107,5 +108,13 @@ def load():
     L.elp_optical_histogram.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
     L.elp_optical_merge.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
     L.elp_print_duplicates_metrics.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    L.elp_bgzf_inflate_bound.restype = C.c_int64
+    L.elp_bgzf_inflate_bound.argtypes = [C.c_void_p, C.c_uint64]
+    L.elp_bgzf_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int]
+    L.elp_bgzf_deflate_bound.restype = C.c_uint64
+    L.elp_bgzf_deflate_bound.argtypes = [C.c_uint64]
+    L.elp_bgzf_deflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int]
+    L.elp_bam_header_size.restype = C.c_int64
+    L.elp_bam_header_size.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(C.c_int32)]
     _lib = L
     return L

@@ -36,6 +36,7 @@ extern "C" {
 #define ELP_ESTATE (-16)     /* entry point called in the wrong phase order */
 #define ELP_ETILE (-17)      /* a QNAME tile/x/y field that strconv.ParseInt rejects (filters/mark-optical-duplicates.go:57-64) */
 #define ELP_EBAM (-18)       /* malformed BAM alignment record, or an RG:Z value that is not an @RG ID */
+#define ELP_EBGZF (-19)      /* malformed BGZF block (header, BC subfield, CRC32 or ISIZE), utils/bgzf/bgzf-files.go:95-127 */
 
 /* sam.SortingOrder (sam/sam-types.go:40-58) */
 #define ELP_SO_KEEP 0
@@ -186,6 +187,18 @@ uint64_t elp_fetch_qual_bytes(elp_ctx *ctx, uint64_t first, uint64_t n);
 uint64_t elp_fetch_bam_bytes(elp_ctx *ctx, uint64_t first, uint64_t n);
 int elp_fetch_bam(elp_ctx *ctx, uint64_t first, uint64_t n, uint8_t *out, uint64_t capacity, uint64_t *record_off);
 int elp_debug_adapt(elp_ctx *ctx, int32_t *upos, int32_t *score);
+
+/* ---- host utilities for callers that hold BAM files in memory: BGZF blocks are independent gzip members,
+ * (de)compressed here on n_threads host threads with zlib (utils/bgzf/bgzf-files.go:95-127 reader, :324-431 writer).  No context,
+ * no GPU.  inflate: data = whole BGZF blocks back to back (an EOF marker block may be among them); bound = exact output size.
+ * deflate: blocks of 0xff00 input bytes, level as zlib (-1 = default), optional EOF marker block (bgzfEOF) at the end.
+ * elp_bam_header_size: length of magic + text + reference list at the start of an inflated BAM file -- the alignment
+ * records for elp_append_bam start there; the references are in BAM refID order, which must be elp_config's contig order. ---- */
+int64_t elp_bgzf_inflate_bound(const uint8_t *data, uint64_t n);                 /* >= 0, or ELP_EBGZF */
+int elp_bgzf_inflate(const uint8_t *data, uint64_t n, uint8_t *out, uint64_t capacity, uint64_t *out_n, int n_threads);
+uint64_t elp_bgzf_deflate_bound(uint64_t n);
+int elp_bgzf_deflate(const uint8_t *data, uint64_t n, uint8_t *out, uint64_t capacity, uint64_t *out_n, int level, int n_threads, int write_eof);
+int64_t elp_bam_header_size(const uint8_t *bam, uint64_t n, int32_t *n_ref_out);  /* -1 if malformed or truncated */
 
 /* ---- measurement ---- */
 uint64_t elp_launch_count(const elp_ctx *ctx);           /* kernels launched by this library since create/reset */

@@ -476,3 +476,40 @@ def test_against_committed_golden_digests(tmp_path):
         ctx.print_duplicates_metrics(p, "elprep filter in out", "T")
         assert hashlib.sha256(open(p).read().encode()).hexdigest()[:24] == exp["metrics"], name
         ctx.close()
+
+
+def test_whole_bam_file_in_memory():
+    """BGZF file bytes -> inflate (host threads) -> header walk -> elp_append_bam -> path -> elp_fetch_bam -> deflate;
+    the result, decoded with Python's gzip and the parseBamAlignment restatement, carries the oracle's FLAGs and QUALs"""
+    import gzip, struct
+    from elprep_b200 import device, bgzf
+    from util import decode_bam, encode_bam
+    w = synth.make_workload(3_000, SMALL, seed=23)
+    o = oracle_pipeline(w)
+    raw, offs = encode_bam(w.batch, w.header)
+    text = b"@HD\tVN:1.6\tSO:unsorted\n"
+    hdr = b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(w.header.SQ)) + b"".join(
+        struct.pack("<i", len(sq["SN"]) + 1) + sq["SN"].encode() + b"\0" + struct.pack("<i", int(sq["LN"])) for sq in w.header.SQ)
+    bam_file = bgzf.deflate(np.concatenate([np.frombuffer(hdr, np.uint8), raw]))
+    # ---- the flow a caller with the file in memory runs
+    plain = bgzf.inflate(bam_file)
+    h0, nref = bgzf.bam_header_size(plain)
+    assert nref == len(w.header.SQ) and h0 == len(hdr)
+    ctx = device.Context(w.header)
+    for ci in range(len(w.header.SQ)):
+        ctx.set_reference(ci, w.contig_bases[ci]); ctx.set_known_sites(ci, w.sites[ci], already_flat=True)
+    ctx.append_bam(plain[h0:], None)
+    ctx.sort_markdup(); ctx.bqsr_gather(); ctx.bqsr_finalize(None); ctx.bqsr_apply()
+    out, _ = ctx.fetch_bam()
+    out_file = bgzf.deflate(np.concatenate([plain[:h0], out]))
+    ctx.close()
+    # ---- check
+    dec = np.frombuffer(gzip.decompress(out_file.tobytes()), np.uint8)
+    assert dec[:h0].tobytes() == hdr
+    body = dec[h0:]
+    offs2, x = [0], 0
+    while x < body.size:
+        x += 4 + int(body[x]) + (int(body[x + 1]) << 8) + (int(body[x + 2]) << 16) + (int(body[x + 3]) << 24); offs2.append(x)
+    b2 = decode_bam(body, np.array(offs2, np.uint64), w.header)
+    assert np.array_equal(b2.flag, o["flag"]) and np.array_equal(b2.qual, o["qual"])
+    assert np.array_equal(b2.pos, w.batch.pos[o["perm"].astype(np.int64)])
