@@ -24,7 +24,8 @@ __device__ __forceinline__ uint32_t rd16(const uint8_t* p) { return (uint32_t)p[
 
 struct BamArgs {
     uint64_t n, n0;                       // records in this call, reads already in the context
-    const uint8_t* raw; const uint64_t* rec_off;
+    const uint8_t* raw; const uint64_t* start; uint64_t n_bytes;   // start[i]: offset of record i's block_size field
+    int chained;                          // start[] has n + 1 entries and start[i + 1] must be the end of record i (no filter ran)
     int32_t *refid, *pos, *nref, *pnext, *tlen, *rg; uint16_t* flag; uint8_t* mapq;
     uint32_t *len_qname, *len_cigar, *len_seq, *len_qual;   // [n] lengths, scanned afterwards
     const uint8_t* rg_names; const uint32_t* rg_name_off; int n_rg; int n_contigs;
@@ -37,12 +38,11 @@ constexpr int BAM_FIXED = 36;
 __global__ void __launch_bounds__(256) bam_fixed_kernel(BamArgs A) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n) return;
-    const uint8_t* r = A.raw + A.rec_off[i];
-    const uint64_t rec_len = A.rec_off[i + 1] - A.rec_off[i];
+    const uint64_t st = A.start[i];
+    const uint8_t* r = A.raw + st;
     uint32_t bad = 0;
-    if (rec_len < BAM_FIXED) { atomicOr(A.err, DERR_BAM); A.len_qname[i] = A.len_cigar[i] = A.len_seq[i] = A.len_qual[i] = 0; return; }
-    const uint32_t block_size = rd32(r);
-    if ((uint64_t)block_size + 4 != rec_len) bad = 1;
+    const uint64_t rec_len = (st + 4 <= A.n_bytes) ? (uint64_t)rd32(r) + 4 : 0;      // block_size counts the bytes after itself
+    if (rec_len < BAM_FIXED || st + rec_len > A.n_bytes || (A.chained && A.start[i + 1] != st + rec_len)) { atomicOr(A.err, DERR_BAM); A.len_qname[i] = A.len_cigar[i] = A.len_seq[i] = A.len_qual[i] = 0; return; }
     const int32_t refid = (int32_t)rd32(r + 4), pos = (int32_t)rd32(r + 8);
     const uint32_t l_name = r[12], mapq = r[13], n_cig = rd16(r + 16), flag = rd16(r + 18);
     const int32_t l_seq = (int32_t)rd32(r + 20), nref = (int32_t)rd32(r + 24), pnext = (int32_t)rd32(r + 28), tlen = (int32_t)rd32(r + 32);
@@ -101,9 +101,38 @@ __global__ void __launch_bounds__(256) bam_fixed_kernel(BamArgs A) {
     A.len_seq[i] = bad ? 0 : (uint32_t)((l_seq + 1) >> 1); A.len_qual[i] = bad ? 0 : (uint32_t)l_seq;
 }
 
+// ---- fused per-record filters of the ingest (filters/simple-filters.go:71-103,332-347) ----
+// keep[i] = 1 iff record i passes every requested predicate; also checks that the caller's offsets follow the block_size chain
+__global__ void __launch_bounds__(256) bam_keep_kernel(uint64_t n, const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rec_off, uint64_t n_bytes,
+                                                        uint32_t mask, int32_t min_mapq, uint32_t* __restrict__ keep, uint32_t* __restrict__ err) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t st = rec_off[i], len = rec_off[i + 1] - st;
+    const uint8_t* r = raw + st;
+    if (len < BAM_FIXED || (uint64_t)rd32(r) + 4 != len) { atomicOr(err, DERR_BAM); keep[i] = 0; return; }
+    const int32_t refid = (int32_t)rd32(r + 4), pos = (int32_t)rd32(r + 8) + 1;
+    const uint32_t l_name = r[12], mapq = r[13], n_cig = rd16(r + 16), flag = rd16(r + 18);
+    bool k = true;
+    if ((mask & ELP_FILTER_UNMAPPED) && (flag & F_UNMAPPED)) k = false;                                           // RemoveUnmappedReads :73-75
+    if ((mask & ELP_FILTER_UNMAPPED_STRICT) && ((flag & F_UNMAPPED) || pos == 0 || refid < 0)) k = false;          // RemoveUnmappedReadsStrict :79-83
+    if ((int32_t)mapq < min_mapq) k = false;                                                                      // RemoveMappingQualityLessThan :332-347
+    if (k && (mask & ELP_FILTER_NON_EXACT)) {                                                                     // RemoveNonExactMappingReads :90-99: only M and S
+        const uint64_t c0 = BAM_FIXED + (uint64_t)l_name;
+        if (c0 + 4ull * n_cig > len) { atomicOr(err, DERR_BAM); keep[i] = 0; return; }
+        for (uint32_t q = 0; q < n_cig; q++) { const uint32_t o = r[c0 + 4 * q] & 15u; if (o != 0 && o != 4) { k = false; break; } }
+    }
+    if ((mask & ELP_FILTER_DUPLICATES) && (flag & F_DUPLICATE)) k = false;                                        // RemoveDuplicateReads :131-133 (flags of the input)
+    keep[i] = k ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) bam_compact_kernel(uint64_t n, const uint32_t* __restrict__ keep, const uint64_t* __restrict__ slot, const uint64_t* __restrict__ rec_off,
+                                                           uint64_t* __restrict__ start) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keep[i]) start[slot[i]] = rec_off[i];
+}
+
 struct CopyArgs {
     uint64_t n, n0;
-    const uint8_t* raw; const uint64_t* rec_off;
+    const uint8_t* raw; const uint64_t* start;
     const uint64_t *qname_off, *cigar_off, *seq_off, *qual_off;   // arena-global, indexed n0 + i
     uint8_t* qname; uint32_t* cigar; uint8_t* seq; uint8_t* qual;
 };
@@ -113,7 +142,7 @@ __global__ void __launch_bounds__(256) bam_copy_kernel(CopyArgs A) {
     const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (i >= A.n) return;
     const uint64_t k = A.n0 + i;
-    const uint8_t* r = A.raw + A.rec_off[i];
+    const uint8_t* r = A.raw + A.start[i];
     const uint64_t q0 = A.qname_off[k], q1 = A.qname_off[k + 1], c0 = A.cigar_off[k], c1 = A.cigar_off[k + 1];
     const uint64_t s0 = A.seq_off[k], s1 = A.seq_off[k + 1], u0 = A.qual_off[k], u1 = A.qual_off[k + 1];
     if (q1 == q0 && c1 == c0 && s1 == s0 && u1 == u0) return;      // rejected record
@@ -133,12 +162,13 @@ __global__ void __launch_bounds__(256) add_base_u64_kernel(uint64_t n, uint64_t*
 }
 
 // ---- egress ----
-__global__ void __launch_bounds__(256) bam_out_len_kernel(uint64_t n, const uint32_t* __restrict__ perm, const uint64_t* __restrict__ all_off, uint32_t* __restrict__ len) {
+__global__ void __launch_bounds__(256) bam_out_len_kernel(uint64_t n, const uint32_t* __restrict__ perm, const uint64_t* __restrict__ all_start, const uint8_t* __restrict__ all,
+                                                           uint32_t* __restrict__ len) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) { const uint32_t i = perm[k]; len[k] = (uint32_t)(all_off[i + 1] - all_off[i]); }
+    if (k < n) len[k] = rd32(all + all_start[perm[k]]) + 4;
 }
 // one warp per output record: copy the stored record, patch FLAG (bytes 18..19 of the record with its block_size) and QUAL
-__global__ void __launch_bounds__(256) bam_out_copy_kernel(uint64_t n, uint64_t first, const uint32_t* __restrict__ perm, const uint64_t* __restrict__ all_off,
+__global__ void __launch_bounds__(256) bam_out_copy_kernel(uint64_t n, uint64_t first, const uint32_t* __restrict__ perm, const uint64_t* __restrict__ all_start,
                                                             const uint8_t* __restrict__ all, const uint64_t* __restrict__ out_off, uint8_t* __restrict__ out,
                                                             const uint16_t* __restrict__ s_flag, const uint64_t* __restrict__ s_out_off, const uint8_t* __restrict__ qual_out) {
     const unsigned lane = threadIdx.x & 31;
@@ -146,8 +176,8 @@ __global__ void __launch_bounds__(256) bam_out_copy_kernel(uint64_t n, uint64_t 
     if (kk >= n) return;
     const uint64_t k = first + kk;
     const uint32_t i = perm[k];
-    const uint8_t* r = all + all_off[i];
-    const uint64_t len = all_off[i + 1] - all_off[i];
+    const uint8_t* r = all + all_start[i];
+    const uint64_t len = (uint64_t)rd32(r) + 4;
     uint8_t* o = out + out_off[kk];
     const uint32_t l_name = r[12], n_cig = rd16(r + 16);
     const int32_t l_seq = (int32_t)rd32(r + 20);
@@ -190,13 +220,35 @@ extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_byt
         n_records = walked.size() - 1;
         record_off = walked.data();
     }
-    const uint64_t bn = n_records;
+    uint64_t bn = n_records;
     if (bn == 0) return ELP_OK;
     if (record_off[bn] != n_bytes) return c->fail(E_INVAL, "elp_append_bam: record_off[n_records] must equal n_bytes");
     for (uint64_t i = 0; i < bn; i++) if (record_off[i + 1] < record_off[i] || record_off[i + 1] > n_bytes) return c->fail(E_INVAL, "elp_append_bam: record_off must be non-decreasing and within n_bytes");
-    const uint64_t n0 = c->n, n1 = n0 + bn;
-    if (n1 >= (1ull << 32)) return c->fail(E_LIMIT, "more than 2^32-1 reads in one context");
+    const uint64_t n0 = c->n;
+    if (n0 + bn >= (1ull << 32)) return c->fail(E_LIMIT, "more than 2^32-1 reads in one context");
     cudaStream_t s = c->stream;
+    const uint64_t nrec = bn;                                 // records handed over; bn becomes the number that pass the filters
+    TRY(grow(c, c->bam_raw, n_bytes + 64, 0)); TRY(grow(c, c->bam_off, nrec + 2, 0)); TRY(grow(c, c->bam_start, nrec + 2, 0));
+    CUDA_TRY(c, cudaMemcpyAsync(c->bam_raw.p, records, n_bytes, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->bam_off.p, record_off, (nrec + 1) * 8, cudaMemcpyHostToDevice, s));
+    const uint64_t* d_start = c->bam_off.p;                   // without filters: record i is read n0 + i
+    if (c->filter_mask || c->filter_min_mapq > 0) {
+        TRY(grow(c, c->scan_tmp, nrec + 8, 0)); TRY(grow(c, c->off_stage, nrec + 2, 0));
+        c->begin("bam_keep", (double)nrec * 48);
+        bam_keep_kernel<<<nblk(nrec, 256), 256, 0, s>>>(nrec, c->bam_raw.p, c->bam_off.p, n_bytes, c->filter_mask, c->filter_min_mapq, c->scan_tmp.p, c->d_err);
+        c->end(); LAUNCH_CHECK(c);
+        TRY(exclusive_scan_u32_to_u64(c, c->scan_tmp.p, c->off_stage.p, nrec));
+        bam_compact_kernel<<<nblk(nrec, 256), 256, 0, s>>>(nrec, c->scan_tmp.p, c->off_stage.p, c->bam_off.p, c->bam_start.p); c->launches++;
+        LAUNCH_CHECK(c);
+        uint64_t kept = 0;
+        CUDA_TRY(c, cudaMemcpyAsync(&kept, c->off_stage.p + nrec, 8, cudaMemcpyDeviceToHost, s));
+        int rc0 = check_device_errors(c);   // synchronizes
+        if (rc0) return rc0;
+        bn = kept; d_start = c->bam_start.p;
+        c->n_filtered += nrec - kept;
+        if (bn == 0) return ELP_OK;
+    }
+    const uint64_t n1 = n0 + bn;
     // @RG ID strings for the RG:Z match
     if (!c->d_rg_names && c->n_rg) {
         std::vector<uint8_t> names; std::vector<uint32_t> off(1, 0);
@@ -206,15 +258,12 @@ extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_byt
         CUDA_TRY(c, cudaMemcpy(c->d_rg_names, names.data(), names.size(), cudaMemcpyHostToDevice));
         CUDA_TRY(c, cudaMemcpy(c->d_rg_name_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
     }
-    TRY(grow(c, c->bam_raw, n_bytes + 64, 0)); TRY(grow(c, c->bam_off, bn + 2, 0));
     TRY(grow(c, c->refid, n1 + 1, n0)); TRY(grow(c, c->pos, n1 + 1, n0)); TRY(grow(c, c->nref, n1 + 1, n0)); TRY(grow(c, c->pnext, n1 + 1, n0)); TRY(grow(c, c->tlen, n1 + 1, n0));
     TRY(grow(c, c->rg, n1 + 1, n0)); TRY(grow(c, c->flag, n1 + 2, n0)); TRY(grow(c, c->mapq, n1 + 1, n0));
     TRY(grow(c, c->qname_off, n1 + 2, n0 + 1)); TRY(grow(c, c->cigar_off, n1 + 2, n0 + 1)); TRY(grow(c, c->qual_off, n1 + 2, n0 + 1)); TRY(grow(c, c->seq_off, n1 + 2, n0 + 1));
-    TRY(grow(c, c->scan_tmp, 4 * (bn + 4) + 8, 0));
-    CUDA_TRY(c, cudaMemcpyAsync(c->bam_raw.p, records, n_bytes, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->bam_off.p, record_off, (bn + 1) * 8, cudaMemcpyHostToDevice, s));
+    TRY(grow(c, c->scan_tmp, 4 * (bn + 4) + 8, 0));   // (the keep flags above are dead by now)
     BamArgs A{};
-    A.n = bn; A.n0 = n0; A.raw = c->bam_raw.p; A.rec_off = c->bam_off.p;
+    A.n = bn; A.n0 = n0; A.raw = c->bam_raw.p; A.start = d_start; A.n_bytes = n_bytes; A.chained = d_start == c->bam_off.p;
     A.refid = c->refid.p; A.pos = c->pos.p; A.nref = c->nref.p; A.pnext = c->pnext.p; A.tlen = c->tlen.p; A.rg = c->rg.p; A.flag = c->flag.p; A.mapq = c->mapq.p;
     A.len_qname = c->scan_tmp.p; A.len_cigar = c->scan_tmp.p + (bn + 4); A.len_seq = c->scan_tmp.p + 2 * (bn + 4); A.len_qual = c->scan_tmp.p + 3 * (bn + 4);
     A.rg_names = c->d_rg_names; A.rg_name_off = c->d_rg_name_off; A.n_rg = c->n_rg; A.n_contigs = c->n_contigs; A.err = c->d_err;
@@ -237,7 +286,7 @@ extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_byt
     TRY(grow(c, c->qname, ends[0] + 64, c->n_qname)); TRY(grow(c, c->cigar, ends[1] + 16, c->n_cigar));
     TRY(grow(c, c->seq, ends[2] + 64, c->n_seq)); TRY(grow(c, c->qual, ends[3] + 64, c->n_qual));
     CopyArgs B{};
-    B.n = bn; B.n0 = n0; B.raw = c->bam_raw.p; B.rec_off = c->bam_off.p;
+    B.n = bn; B.n0 = n0; B.raw = c->bam_raw.p; B.start = d_start;
     B.qname_off = c->qname_off.p; B.cigar_off = c->cigar_off.p; B.seq_off = c->seq_off.p; B.qual_off = c->qual_off.p;
     B.qname = c->qname.p; B.cigar = c->cigar.p; B.seq = c->seq.p; B.qual = c->qual.p;
     c->begin("bam_copy", 2.0 * (double)n_bytes);
@@ -246,10 +295,10 @@ extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_byt
     CUDA_TRY(c, cudaStreamSynchronize(s));   // the caller's buffer may be released after return (cgo pointer rules)
     // keep the raw records for elp_fetch_bam (only meaningful while every read of the context came in as BAM)
     if (c->bam_reads == n0) {
-        TRY(grow(c, c->bam_all, c->n_bam + n_bytes + 64, c->n_bam)); TRY(grow(c, c->bam_all_off, n1 + 2, n0 + 1));
+        TRY(grow(c, c->bam_all, c->n_bam + n_bytes + 64, c->n_bam)); TRY(grow(c, c->bam_all_off, n1 + 2, n0));
         CUDA_TRY(c, cudaMemcpyAsync(c->bam_all.p + c->n_bam, c->bam_raw.p, n_bytes, cudaMemcpyDeviceToDevice, s));
-        CUDA_TRY(c, cudaMemcpyAsync(c->bam_all_off.p + n0, c->bam_off.p, (bn + 1) * 8, cudaMemcpyDeviceToDevice, s));
-        if (c->n_bam) { add_base_u64_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->bam_all_off.p + n0, c->n_bam); c->launches++; }
+        CUDA_TRY(c, cudaMemcpyAsync(c->bam_all_off.p + n0, d_start, bn * 8, cudaMemcpyDeviceToDevice, s));      // start of every kept record
+        if (c->n_bam) { add_base_u64_kernel<<<nblk(bn, 256), 256, 0, s>>>(bn, c->bam_all_off.p + n0, c->n_bam); c->launches++; }
         CUDA_TRY(c, cudaStreamSynchronize(s));
         c->n_bam += n_bytes; c->bam_reads = n1;
     }
@@ -263,7 +312,7 @@ static int bam_out_prepare(elp_ctx* c, uint64_t first, uint64_t n, uint64_t* tot
     if (c->bam_reads != c->n) return c->fail(E_STATE, "elp_fetch_bam: not every read of this context came in through elp_append_bam");
     if (first + n > c->n) return c->fail(E_INVAL, "elp_fetch_bam: range [%llu,%llu) exceeds %llu reads", (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)c->n);
     TRY(grow(c, c->scan_tmp, n + 8, 0)); TRY(grow(c, c->off_stage, n + 2, 0));
-    bam_out_len_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->perm.p + first, c->bam_all_off.p, c->scan_tmp.p); c->launches++;
+    bam_out_len_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->perm.p + first, c->bam_all_off.p, c->bam_all.p, c->scan_tmp.p); c->launches++;
     LAUNCH_CHECK(c);
     TRY(exclusive_scan_u32_to_u64(c, c->scan_tmp.p, c->off_stage.p, n));
     CUDA_TRY(c, cudaMemcpyAsync(total, c->off_stage.p + n, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -296,3 +345,11 @@ extern "C" int elp_fetch_bam(elp_ctx* c, uint64_t first, uint64_t n, uint8_t* ou
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ELP_OK;
 }
+
+extern "C" int elp_set_ingest_filter(elp_ctx* c, uint32_t mask, int32_t min_mapq) {
+    if (!c) return ELP_EINVAL;
+    if (mask & ~(uint32_t)(ELP_FILTER_UNMAPPED | ELP_FILTER_UNMAPPED_STRICT | ELP_FILTER_NON_EXACT | ELP_FILTER_DUPLICATES)) return c->fail(E_INVAL, "elp_set_ingest_filter: unknown filter bits 0x%x", mask);
+    c->filter_mask = mask; c->filter_min_mapq = min_mapq;
+    return ELP_OK;
+}
+extern "C" uint64_t elp_n_filtered(const elp_ctx* c) { return c ? c->n_filtered : 0; }

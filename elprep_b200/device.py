@@ -91,6 +91,12 @@ class Context:
         b.l_seq = _vp(batch.lseq)
         self._ck(self.L.elp_append_batch(self.h, C.byref(b)))
 
+    def set_ingest_filter(self, mask=0, min_mapq=0):
+        self._ck(self.L.elp_set_ingest_filter(self.h, mask, min_mapq))
+
+    def n_filtered(self):
+        return int(self.L.elp_n_filtered(self.h))
+
     def append_bam(self, records, record_off=None):
         """records: uint8 array of consecutive BAM alignment records (each with its block_size); record_off: uint64[n+1] or None"""
         rec = np.ascontiguousarray(records, dtype=np.uint8)

@@ -45,6 +45,45 @@ def AddREFID(header):
     return None
 
 
+# ---- per-record filters of phase 1 (filters/simple-filters.go), as column predicates for the elp_append_batch path.
+# With elp_append_bam the same predicates run fused into the device ingest (elp_set_ingest_filter). ----
+def _keep(batch, mask):
+    return batch if bool(mask.all()) else batch.take(np.nonzero(mask)[0])
+
+
+def RemoveUnmappedReads(header):
+    """filters.RemoveUnmappedReads (simple-filters.go:73-75)"""
+    return lambda batch: _keep(batch, (batch.flag & sam.Unmapped) == 0)
+
+
+def RemoveUnmappedReadsStrict(header):
+    """filters.RemoveUnmappedReadsStrict (simple-filters.go:79-83): FLAG 0x4, POS 0 or RNAME *"""
+    return lambda batch: _keep(batch, ((batch.flag & sam.Unmapped) == 0) & (batch.pos != 0) & (batch.refid >= 0))
+
+
+def RemoveNonExactMappingReads(header):
+    """filters.RemoveNonExactMappingReads (simple-filters.go:90-99): only M and S operations"""
+    def flt(batch):
+        op = batch.cigar & 15
+        bad = ((op != 0) & (op != 4)).astype(np.int64)
+        cs = np.concatenate([[0], np.cumsum(bad)])
+        off = batch.cigar_off.astype(np.int64)
+        return _keep(batch, (cs[off[1:]] - cs[off[:-1]]) == 0)
+    return flt
+
+
+def RemoveMappingQualityLessThan(mq):
+    """filters.RemoveMappingQualityLessThan (simple-filters.go:332-347) -> Filter"""
+    if mq == 0:
+        return None
+    return lambda header: (lambda batch: _keep(batch, batch.mapq.astype(np.int64) >= mq))
+
+
+def RemoveDuplicateReads(header):
+    """filters.RemoveDuplicateReads (simple-filters.go:131-133)"""
+    return lambda batch: _keep(batch, (batch.flag & sam.Duplicate) == 0)
+
+
 def MarkDuplicates(alsoOpticals):
     """filters.MarkDuplicates (filters/mark-duplicates.go:406-445). Returns (filter, fragments, pairs); the two maps live on
     the device and are only handles here."""

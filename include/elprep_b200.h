@@ -115,6 +115,17 @@ int elp_append_batch(elp_ctx *ctx, const elp_batch *batch);
  * 1-based; the RG:Z tag is matched against elp_config.rg_id (an unknown value is ELP_EBAM, no RG tag is rg = -1).
  * Not supported: the CG:B long-CIGAR convention (ELP_ELIMIT).  Thread-safe like elp_append_batch. */
 int elp_append_bam(elp_ctx *ctx, const uint8_t *records, uint64_t n_bytes, const uint64_t *record_off, uint64_t n_records);
+/* Per-record filters fused into elp_append_bam: a record that fails a requested predicate never becomes a read
+ * of the context (later calls; elp_n_filtered counts them).  filters/simple-filters.go: RemoveUnmappedReads (:73-75),
+ * RemoveUnmappedReadsStrict (:79-83: FLAG 0x4, POS 0 or RNAME *), RemoveNonExactMappingReads (:90-99: only M and S operations),
+ * RemoveMappingQualityLessThan (:332-347: keeps MAPQ >= min_mapq), RemoveDuplicateReads (:131-133, on the FLAG the record comes
+ * in with).  With elp_append_batch the caller's marshaller applies its filters to the []*Alignment before building columns. */
+#define ELP_FILTER_UNMAPPED 1u
+#define ELP_FILTER_UNMAPPED_STRICT 2u
+#define ELP_FILTER_NON_EXACT 4u
+#define ELP_FILTER_DUPLICATES 8u
+int elp_set_ingest_filter(elp_ctx *ctx, uint32_t mask, int32_t min_mapq);
+uint64_t elp_n_filtered(const elp_ctx *ctx);
 uint64_t elp_n_reads(const elp_ctx *ctx);
 
 /* filters.MarkDuplicates (filters/mark-duplicates.go:406-445) + By(CoordinateLess).ParallelStableSort in the

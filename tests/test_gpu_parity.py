@@ -513,3 +513,48 @@ def test_whole_bam_file_in_memory():
     b2 = decode_bam(body, np.array(offs2, np.uint64), w.header)
     assert np.array_equal(b2.flag, o["flag"]) and np.array_equal(b2.qual, o["qual"])
     assert np.array_equal(b2.pos, w.batch.pos[o["perm"].astype(np.int64)])
+
+
+def test_bam_ingest_filters():
+    """per-record filters fused into elp_append_bam (filters/simple-filters.go:71-103,131-133,332-347): the reads that survive, and
+    everything computed from them, equal the column path over the host-filtered batch"""
+    from elprep_b200 import device, _lib
+    from util import encode_bam
+    w = synth.make_workload(5_000, SMALL, seed=29, unmapped_frac=0.1)
+    b = w.batch
+    b.flag[::17] |= 0x400                                     # duplicate flags on input, for RemoveDuplicateReads
+    raw, offs = encode_bam(b, w.header)
+    ncig = (b.cigar_off[1:] - b.cigar_off[:-1]).astype(np.int64)
+    ops_ok = np.ones(b.n, bool)
+    for i in np.nonzero(ncig > 0)[0]:
+        ops = b.cigar[int(b.cigar_off[i]):int(b.cigar_off[i + 1])] & 15
+        ops_ok[i] = bool(np.all((ops == 0) | (ops == 4)))
+    preds = {
+        _lib.FILTER_UNMAPPED: (b.flag & 4) == 0,
+        _lib.FILTER_UNMAPPED_STRICT: ((b.flag & 4) == 0) & (b.pos != 0) & (b.refid >= 0),
+        _lib.FILTER_NON_EXACT: ops_ok,
+        _lib.FILTER_DUPLICATES: (b.flag & 0x400) == 0,
+    }
+    cases = [(m, 0) for m in preds] + [(0, 30), (_lib.FILTER_UNMAPPED | _lib.FILTER_NON_EXACT | _lib.FILTER_DUPLICATES, 20), (0, 300)]
+    for mask, mq in cases:
+        keep = b.mapq.astype(np.int64) >= mq
+        for bit, p in preds.items():
+            if mask & bit:
+                keep &= p
+        sub = b.take(np.nonzero(keep)[0])
+        ctx = device.Context(w.header)
+        ctx.set_ingest_filter(mask, mq)
+        half = b.n // 2
+        ctx.append_bam(raw[:int(offs[half])], offs[:half + 1])
+        ctx.append_bam(raw[int(offs[half]):], None)
+        assert ctx.n == sub.n and ctx.n_filtered() == b.n - sub.n, (mask, mq)
+        ref = device.Context(w.header)
+        ref.append(sub)
+        for c_ in (ctx, ref):
+            c_.sort_markdup()
+        a1, a2 = ctx.fetch(), ref.fetch()
+        assert all(np.array_equal(x, y) for x, y in zip(a1, a2)), (mask, mq)
+        if sub.n:
+            out, ooff = ctx.fetch_bam()
+            assert ooff.size == sub.n + 1 and int(ooff[-1]) == out.size
+        ctx.close(); ref.close()

@@ -41,3 +41,22 @@ def test_header_tables():
     assert h.refid_table() == {"*": -1, "a": 0, "b": 1}
     b = sam.AlignmentBatch.from_records(h, [dict(QNAME="q", RNAME="b", RNEXT="=", POS=3, CIGAR="2M1M", SEQ="ACG", QUAL=[1, 2, 3], RG="r2")])
     assert b.refid[0] == 1 and b.nref[0] == 1 and sam.decode_cigar(b.cigar) == "3M"               # adjacent identical ops merge (sam-types.go:708-710)
+
+
+def test_simple_filters_as_column_predicates():
+    """filters/simple-filters.go:71-103,131-133,332-347 over an AlignmentBatch"""
+    from elprep_b200 import filters
+    h = sam.Header(sq=[{"SN": "chr1", "LN": 1000}], rg=[{"ID": "rg1"}])
+    recs = [dict(QNAME="a", FLAG=0, RNAME="chr1", POS=5, MAPQ=60, CIGAR="4M", SEQ="ACGT", QUAL=[30] * 4),
+            dict(QNAME="b", FLAG=4, RNAME="*", POS=0, MAPQ=0, CIGAR="*", SEQ="ACGT", QUAL=[30] * 4),
+            dict(QNAME="c", FLAG=0, RNAME="chr1", POS=0, MAPQ=10, CIGAR="2S2M", SEQ="ACGT", QUAL=[30] * 4),      # mapped by FLAG, POS 0
+            dict(QNAME="d", FLAG=0x400, RNAME="chr1", POS=9, MAPQ=29, CIGAR="2M1I1M", SEQ="ACGT", QUAL=[30] * 4),
+            dict(QNAME="e", FLAG=16, RNAME="chr1", POS=9, MAPQ=30, CIGAR="1H4M", SEQ="ACGT", QUAL=[30] * 4)]
+    b = sam.AlignmentBatch.from_records(h, recs)
+    names = lambda x: [x.qname_str(i) for i in range(x.n)]
+    assert names(filters.RemoveUnmappedReads(h)(b)) == ["a", "c", "d", "e"]
+    assert names(filters.RemoveUnmappedReadsStrict(h)(b)) == ["a", "d", "e"]
+    assert names(filters.RemoveNonExactMappingReads(h)(b)) == ["a", "b", "c"]
+    assert names(filters.RemoveMappingQualityLessThan(30)(h)(b)) == ["a", "e"] and filters.RemoveMappingQualityLessThan(0) is None
+    assert names(filters.RemoveDuplicateReads(h)(b)) == ["a", "b", "c", "e"]
+    assert filters.RemoveUnmappedReads(h)(b.take([0, 3])) .n == 2
