@@ -263,10 +263,9 @@ int elp_sort_markdup(elp_ctx* c, int sorting_order, int mark_duplicates) {
     if (!c) return ELP_EINVAL;
     cudaSetDevice(c->device);
     if (c->sorted) return c->fail(E_STATE, "elp_sort_markdup called twice (call elp_reset first)");
-    if (sorting_order == ELP_SO_QUERYNAME) return c->fail(E_INVAL, "queryname order is not on the device path");
     if (mark_duplicates != 0 && mark_duplicates != ELP_MARKDUP && mark_duplicates != ELP_MARKDUP_OPTICAL) return c->fail(E_INVAL, "elp_sort_markdup: mark_duplicates must be 0, ELP_MARKDUP or ELP_MARKDUP_OPTICAL");
     if (mark_duplicates) TRY(phase_markdup(c, mark_duplicates == ELP_MARKDUP_OPTICAL));
-    TRY(phase_coordinate_sort(c, sorting_order == ELP_SO_COORDINATE));
+    TRY(phase_coordinate_sort(c, sorting_order == ELP_SO_COORDINATE ? 1 : (sorting_order == ELP_SO_QUERYNAME ? 2 : 0)));
     return ELP_OK;
 }
 

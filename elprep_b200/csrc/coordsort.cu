@@ -161,7 +161,8 @@ __global__ void __launch_bounds__(256) lseq_u32_kernel(uint64_t n, const int32_t
 
 }  // namespace
 
-int phase_coordinate_sort(elp_ctx* c, bool sort) {
+int phase_coordinate_sort(elp_ctx* c, int order) {   // 0 keep, 1 coordinate, 2 queryname
+    const bool sort = order == 1;
     const uint64_t n = c->n;
     int rc = phase_adapt(c);   // value ranges (pos_max) size the key
     if (rc) return rc;
@@ -228,6 +229,26 @@ int phase_coordinate_sort(elp_ctx* c, bool sort) {
         }
         CUDA_TRY(c, cudaMemcpyAsync(c->perm.p, vals, n * 4, cudaMemcpyDeviceToDevice, c->stream));
 
+    } else if (order == 2 && n > 1) {
+        // By(QNAMELess).ParallelStableSort (sam/sam-types.go:479-481, sam/filter-pipeline.go:119-123): stable LSD radix sort over
+        // 8-byte big-endian chunks of the QNAME, last chunk first (names are zero padded: a prefix sorts before its extensions)
+        CUDA_TRY(c, c->keys_a.reserve(2 * n + 4, c->stream)); CUDA_TRY(c, c->keys_b.reserve(2 * n + 4, c->stream));
+        CUDA_TRY(c, c->vals_a.reserve(n + 4, c->stream)); CUDA_TRY(c, c->vals_b.reserve(n + 4, c->stream));
+        TieCols tc{c->flag.p, c->mapq.p, c->nref.p, c->pnext.p, c->tlen.p, c->qname_off.p, c->qname.p};
+        CoordLayout L{};
+        const int nq = std::max(1, (int)((c->h_ranges.qname_max + 7) / 8));
+        iota_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->vals_a.p); c->launches++; LAUNCH_CHECK(c);
+        const uint32_t* elem = c->vals_a.p;
+        for (int ch = 0; ch < nq; ch++) {
+            c->begin("qname_chunk_keys", (double)n * 32);
+            chunk_keys_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, elem, 3 + ch, nq, tc, nullptr, nullptr, c->refid.p, c->pos.p, L, c->keys_a.p, c->vals_a.p);
+            c->end(); LAUNCH_CHECK(c);
+            bool b2 = false;
+            rc = radix_sort_u64(c, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, 64, &b2, "u64");
+            if (rc) return rc;
+            elem = b2 ? c->vals_b.p : c->vals_a.p;
+        }
+        CUDA_TRY(c, cudaMemcpyAsync(c->perm.p, elem, n * 4, cudaMemcpyDeviceToDevice, c->stream));
     } else if (n) {
         iota_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->perm.p);
         c->launches++; LAUNCH_CHECK(c);

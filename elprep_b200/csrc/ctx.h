@@ -202,7 +202,7 @@ int exclusive_scan_u64(elp_ctx* c, const uint64_t* in, uint64_t* out, uint64_t n
 int phase_adapt(elp_ctx* c);
 int phase_markdup(elp_ctx* c, bool optical);
 int phase_optical(elp_ctx* c, uint64_t npairs, const uint64_t* sorted_keys, const uint32_t* sorted_vals, int bS);
-int phase_coordinate_sort(elp_ctx* c, bool sort);
+int phase_coordinate_sort(elp_ctx* c, int order);   // 0 keep, 1 coordinate, 2 queryname
 int phase_bqsr_gather(elp_ctx* c);
 int phase_bqsr_finalize(elp_ctx* c, const char* report_path);
 int phase_bqsr_apply(elp_ctx* c);

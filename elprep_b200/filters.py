@@ -150,8 +150,6 @@ class DeviceSam:
 
     # -- PipelineOutput.AddNodes (sam/filter-pipeline.go:108-128): receive batches, sort in the Finalize
     def AddNodes(self, header, sorting_order, batches, alignment_filters):
-        if sorting_order == sam.Queryname:
-            raise ValueError("queryname order is not on the device path")
         self.Header = header
         self._markdup = any(isinstance(a, _DeviceOp) and a.kind == "markdup" for a in alignment_filters)
         host_filters = [a for a in alignment_filters if not isinstance(a, _DeviceOp)]
@@ -161,7 +159,7 @@ class DeviceSam:
                 b = a(b)
             self._batches.append(b)
             self.ctx.append(b)
-        so = device.SO_COORDINATE if sorting_order == sam.Coordinate else device.SO_KEEP
+        so = device.SO_COORDINATE if sorting_order == sam.Coordinate else (_lib_const("SO_QUERYNAME") if sorting_order == sam.Queryname else device.SO_KEEP)
         opticals = any(isinstance(a, _DeviceOp) and a.kind == "markdup" and a.kw["alsoOpticals"] for a in alignment_filters)
         self.ctx.sort_markdup(so, (2 if opticals else 1) if self._markdup else 0)           # the Finalize node
 
@@ -263,6 +261,11 @@ class BaseRecalibratorTables:
                 self.FinalizeBQSRTables()
             return _DeviceOp("apply")
         return flt
+
+
+def _lib_const(name):
+    from . import _lib
+    return getattr(_lib, name)
 
 
 def ctx_quantize(ctx):

@@ -130,7 +130,8 @@ uint64_t elp_n_reads(const elp_ctx *ctx);
 
 /* filters.MarkDuplicates (filters/mark-duplicates.go:406-445) + By(CoordinateLess).ParallelStableSort in the
  * Finalize of (*sam.Sam).AddNodes (sam/filter-pipeline.go:113-117, sam/sam-types.go:425-473,639-641).
- * sorting_order: ELP_SO_COORDINATE sorts; KEEP/UNKNOWN/UNSORTED leave arrival order.
+ * sorting_order: ELP_SO_COORDINATE sorts by CoordinateLess; ELP_SO_QUERYNAME by QNAMELess (sam-types.go:479-481, stable);
+ * KEEP/UNKNOWN/UNSORTED leave arrival order.
  * mark_duplicates: 0 none, ELP_MARKDUP = MarkDuplicates(false), ELP_MARKDUP_OPTICAL = MarkDuplicates(true) followed by
  * filters.MarkOpticalDuplicates(reads, pairs, optical_pixel_distance) (filters/mark-optical-duplicates.go:468-517,
  * cmd/filter.go:782) -- the metrics are read with the elp_optical_* calls below. */

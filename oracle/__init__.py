@@ -129,6 +129,13 @@ def coordinate_sort(batch, n_threads=1):
     return perm
 
 
+def queryname_sort(batch):
+    r = OracleReads(batch)
+    perm = np.zeros(batch.n, dtype=np.int64)
+    lib().orc_queryname_sort(C.byref(r.s), _p(perm))
+    return perm
+
+
 def coordinate_less(batch, a, b):
     r = OracleReads(batch)
     return bool(lib().orc_coordinate_less(C.byref(r.s), C.c_int64(a), C.c_int64(b)))

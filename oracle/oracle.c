@@ -187,6 +187,24 @@ int orc_coordinate_sort(const orc_reads *r, int64_t *perm, int nt) {
     return 0;
 }
 
+/* sam/sam-types.go:479-481 + sam/filter-pipeline.go:119-123: By(QNAMELess) stable sort; perm[k] = index of k-th record */
+int orc_queryname_sort(const orc_reads *r, int64_t *perm) {
+    int64_t n = r->n;
+    int64_t *tmp = (int64_t *)malloc(sizeof(int64_t) * (n > 0 ? n : 1));
+    for (int64_t i = 0; i < n; i++) perm[i] = i;
+    for (int64_t w = 1; w < n; w *= 2) {            /* bottom-up stable merge sort */
+        for (int64_t lo = 0; lo < n; lo += 2 * w) {
+            int64_t mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n, i = lo, j = mid, k = lo;
+            while (i < mid && j < hi) { if (qname_cmp(r, perm[j], perm[i]) < 0) tmp[k++] = perm[j++]; else tmp[k++] = perm[i++]; }
+            while (i < mid) tmp[k++] = perm[i++];
+            while (j < hi) tmp[k++] = perm[j++];
+        }
+        memcpy(perm, tmp, sizeof(int64_t) * n);
+    }
+    free(tmp);
+    return 0;
+}
+
 /* ---------------------------------------------- sharded concurrent map (pargo sync.Map semantics) */
 typedef struct mnode { struct mnode *next; uint64_t hash; int64_t keyref; void *val; } mnode;
 typedef struct { pthread_mutex_t mu; mnode **buckets; int64_t nb, count; mnode *freelist; char pad[24]; } mshard;

@@ -67,6 +67,8 @@ uint16_t orc_mod_flag(uint16_t flag);
 int orc_coordinate_less(const orc_reads *r, int64_t a, int64_t b);
 /* sam/sam-types.go:599-641 + sam/filter-pipeline.go:113-117: perm[k] = index of k-th record in sorted order */
 int orc_coordinate_sort(const orc_reads *r, int64_t *perm, int n_threads);
+/* sam/sam-types.go:479-481: By(QNAMELess) stable sort */
+int orc_queryname_sort(const orc_reads *r, int64_t *perm);
 /* filters/mark-duplicates.go:406-445 (+ adapt/classifyFragment/classifyPair). Sets 0x400 in r->flag.
  * upos_out/score_out optional (may be NULL). returns 0, or -1 on "Invalid QUAL character". */
 int orc_mark_duplicates(const orc_reads *r, const orc_header *h, int n_threads, int32_t *upos_out, int32_t *score_out);

@@ -558,3 +558,39 @@ def test_bam_ingest_filters():
             out, ooff = ctx.fetch_bam()
             assert ooff.size == sub.n + 1 and int(ooff[-1]) == out.size
         ctx.close(); ref.close()
+
+
+def test_queryname_order():
+    """--sorting-order queryname: By(QNAMELess).ParallelStableSort (sam/sam-types.go:479-481) on the device; duplicate marking and
+    BQSR are order independent"""
+    import oracle
+    from elprep_b200 import device, _lib
+    w = synth.make_workload(8_000, SMALL, seed=31)
+    b = w.batch.copy()
+    oracle.mark_duplicates(b, w.header)
+    perm = oracle.queryname_sort(b)
+    srt = b.take(perm)
+    ref = oracle.Reference(w.header, w.contig_bases, w.sites)
+    t = oracle.bqsr_gather(srt, w.header, ref, n_threads=4)
+    oracle.bqsr_finalize(t); oracle.bqsr_apply(srt, w.header, t, n_threads=4)
+    ctx = device.Context(w.header)
+    for ci in range(len(w.header.SQ)):
+        ctx.set_reference(ci, w.contig_bases[ci]); ctx.set_known_sites(ci, w.sites[ci], already_flat=True)
+    half = w.batch.n // 2
+    ctx.append(w.batch.take(np.arange(0, half))); ctx.append(w.batch.take(np.arange(half, w.batch.n)))
+    ctx.sort_markdup(_lib.SO_QUERYNAME, True)
+    ctx.bqsr_gather(); ctx.bqsr_finalize(None); ctx.bqsr_apply()
+    idx, flag, qoff, qual = ctx.fetch()
+    assert np.array_equal(idx, perm.astype(np.uint64)) and np.array_equal(flag, srt.flag)
+    assert np.array_equal(qual[:int(qoff[-1])], srt.qual)
+    d, _ = oracle_tables_dense(t, 500)
+    assert np.array_equal(ctx.tables_get(), d)
+    ctx.close()
+    # names of different lengths, prefixes, equal names (stability)
+    h = sam.Header(sq=[{"SN": "chr1", "LN": 1000}])
+    names = ["r10", "r2", "r1", "r1", "r", "R9", "r1:x", "a" * 40, "a" * 39 + "b", "a" * 40]
+    bb = sam.AlignmentBatch.from_records(h, [dict(QNAME=q, FLAG=0, RNAME="chr1", POS=10 - i) for i, q in enumerate(names)])
+    ctx = device.Context(h)
+    ctx.append(bb); ctx.sort_markdup(_lib.SO_QUERYNAME, False)
+    assert np.array_equal(ctx.fetch(want_qual=False)[0], oracle.queryname_sort(bb).astype(np.uint64))
+    ctx.close()

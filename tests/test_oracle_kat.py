@@ -268,3 +268,12 @@ def test_empirical_quality(orc):
         mis = int(obs * 10 ** rng.uniform(-6, -0.3))
         prior = float(rng.choice([rng.integers(2, 60), rng.uniform(2, 60)]))
         assert eq(obs, mis, prior) == _py_empirical(obs, mis, prior), (obs, mis, prior)
+
+
+def test_queryname_order(orc):
+    # By(QNAMELess).ParallelStableSort (sam-types.go:479-481): bytewise QNAME order, a prefix first, equal names keep arrival order
+    h = _hdr()
+    recs = [dict(QNAME=q, FLAG=f, RNAME="chr1", POS=p) for q, f, p in
+            [("r10", 0, 5), ("r2", 0, 9), ("r1", 16, 7), ("r1", 0, 3), ("r", 0, 1), ("R9", 0, 2), ("r1:x", 0, 4)]]
+    b = sam.AlignmentBatch.from_records(h, recs)
+    assert list(orc.queryname_sort(b)) == [5, 4, 2, 3, 0, 6, 1]
