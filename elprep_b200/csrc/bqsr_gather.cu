@@ -23,10 +23,7 @@ namespace {
 
 constexpr int MAXC = 64;        // CIGAR operations per read handled by the kernel
 constexpr int MAXIT = 16;       // 32*MAXIT = 512 bases per clipped read (cycles beyond max_cycle=500 are an error anyway)
-#ifndef EXP_WARPS
-#define EXP_WARPS 8
-#endif
-constexpr int WARPS_PER_BLOCK = EXP_WARPS;
+constexpr int WARPS_PER_BLOCK = 8;
 
 __device__ __forceinline__ int op_of(uint32_t c) { return (int)(c & 15); }
 __device__ __forceinline__ int len_of(uint32_t c) { return (int)(c >> 4); }
@@ -328,14 +325,9 @@ __device__ __noinline__ void count_rare(const GatherArgs& A, int cov, int q, int
 }
 
 // shared memory through explicit 32-bit shared-window addresses (generic pointers cost an address conversion per access)
-__device__ __forceinline__ int lds_s8(uint32_t a) { int v; asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void reds_inc(uint32_t a) { asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(a) : "memory"); }
 __device__ __forceinline__ void reds_add(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-// predicated form: no branch around the update
-__device__ __forceinline__ void reds_inc_if(uint32_t a, uint32_t p) {
-    asm volatile("{\n\t.reg .pred pp;\n\tsetp.ne.u32 pp, %1, 0;\n\t@pp red.shared.add.u32 [%0], 1;\n\t}" ::"r"(a), "r"(p) : "memory");
-}
 
 // ---------------------------------------------------------------- kernel B: 16 consecutive bases per lane (the common case)
 // Reads whose clipped CIGAR is one M run (DF_LEAN, > 90 % of a WGS sample).  A warp takes 32 / lanes_per_read consecutive
@@ -698,16 +690,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2048 / (WARPS_PER_BLOCK 
             const uint32_t ctx = ((pcode ^ cmask) & 3u) | (((code ^ cmask) & 3u) << 2);   // key>>4 = prev | cur<<2 (bqsr.go:64-76), complemented for reverse reads
             if (counted && q <= 93 && !badc) {
                 if (slot >= 0) {
-#ifndef EXP_NO_OBS
                     const uint32_t row = (row0 + (uint32_t)slot) * (uint32_t)ncols_s;
                     atomicAdd(&sm_tab[row + (uint32_t)(cyc + Lc)], 1u);
                     if (okc) atomicAdd(&sm_tab[row + (uint32_t)(2 * Lc + 1) + ctx], 1u);
-#endif
                 } else {
                     atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_cycle(cyc)), 1ull);
                     if (okc) atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_ctx((int)ctx)), 1ull);
                 }
-#ifndef EXP_NO_MIS
                 if (snp) {
                     if (slot >= 0) {   // mismatches are sparse (~0.5 % of bases): shared atomics on the CTA's second table
                         const uint32_t row = (row0 + (uint32_t)slot) * (uint32_t)ncols_s;
@@ -718,7 +707,6 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 2048 / (WARPS_PER_BLOCK 
                         if (okc) atomicAdd(A.tables + 2 * A.geom.idx((int)cov, (int)q, A.geom.col_ctx((int)ctx)) + 1, 1ull);
                     }
                 }
-#endif
             }
         }
         errbits = __reduce_or_sync(FULL_MASK, errbits);

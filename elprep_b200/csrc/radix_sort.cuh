@@ -153,28 +153,17 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K*
     }
     RS_STAMP(1);
     uint32_t* wh = warp_hist + warp * RADIX;
-#ifdef RS_PREFETCH_VALS
-    // the payload is only needed after the keys are ranked and scattered: pull its lines towards L1 now
-    if (lane < ITEMS && (wbase - lane + lane * 32) < n_valid) asm volatile("prefetch.global.L1 [%0];" ::"l"(vals_in + base + (wbase - lane) + lane * 32));
-#endif
 #pragma unroll
     for (int j = 0; j < ITEMS; j++) {
         const bool valid = (wbase + j * 32) < n_valid;
         const uint32_t d = valid ? key[j].digit(shift, mask) : (0x100u + lane);   // invalid lanes match nobody
         const uint32_t peers = __match_any_sync(FULL_MASK, d);
-#ifdef RS_RANK_ATOM
-        const uint32_t leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) old = atomicAdd(&wh[d], (uint32_t)__popc(peers));   // shared atomics of one warp retire in issue order: no barrier between items
-        old = __shfl_sync(FULL_MASK, old, leader);
-#else
         // every peer reads the running count, then the leader adds the peer count (no atomic with a return value, no shuffle);
         // __syncwarp orders the add before the next item's reads
         const uint32_t old = valid ? wh[d] : 0u;
         __syncwarp();
         if (valid && (peers & lanemask_lt()) == 0) wh[d] = old + (uint32_t)__popc(peers);
         __syncwarp();
-#endif
         rank[j] = old + __popc(peers & lanemask_lt());
     }
     __syncthreads();
@@ -243,9 +232,6 @@ __global__ void __launch_bounds__(THREADS, MIN_CTAS) rs_onesweep_kernel(const K*
                     if (done) break;
                     uint32_t sx = svv[j];
                     while ((sx >> 30) == 0) {   // predecessor not published yet
-#ifdef RS_NANOSLEEP
-                        __nanosleep(RS_NANOSLEEP);
-#endif
                         sx = ld_relaxed_u32(status + (uint64_t)(t - j) * RADIX + tid);
                     }
                     excl += sx & ST_VALMASK;
