@@ -26,7 +26,10 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 
 // ---------------------------------------------------------------- K1 adapt
 // 8 lanes per read (4 reads per warp); QUAL strips are read as aligned 16-byte chunks with byte masks.
-__global__ void __launch_bounds__(256) adapt_kernel(uint64_t n, const uint16_t* __restrict__ flag, const int32_t* __restrict__ pos,
+#ifndef ADAPT_MINB
+#define ADAPT_MINB 5
+#endif
+__global__ void __launch_bounds__(256, ADAPT_MINB) adapt_kernel(uint64_t n, const uint16_t* __restrict__ flag, const int32_t* __restrict__ pos,
                                                      const int32_t* __restrict__ rg, const int32_t* __restrict__ rg_lib, int n_rg,
                                                      const uint64_t* __restrict__ cigar_off, const uint32_t* __restrict__ cigar,
                                                      const uint64_t* __restrict__ qual_off, const uint8_t* __restrict__ qual,

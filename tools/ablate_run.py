@@ -14,7 +14,7 @@ ctx = device.Context(w.header, profile=True)
 for ci in range(len(contigs)):
     ctx.set_reference(ci, w.contig_bases[ci]); ctx.set_known_sites(ci, w.sites[ci], True)
 for rep in range(3):
-    ctx.reset(); ctx.append(hb); ctx.sort_markdup(); ctx.reset_stats(); ctx.bqsr_gather(); ctx.bqsr_finalize(None); ctx.bqsr_apply(); ctx.synchronize()
+    ctx.reset(); ctx.append(hb); ctx.reset_stats(); ctx.sort_markdup(); ctx.bqsr_gather(); ctx.bqsr_finalize(None); ctx.bqsr_apply(); ctx.synchronize()
 st = ctx.kernel_stats()
 print(os.environ.get("ELPREP_B200_LIB","default").split("/")[-1], "  ".join("%%s %%.2f" %% (k, st[k]["ms"]) for k in ("bqsr_gather", "bqsr_gather_indel", "bqsr_gather_general", "bqsr_gen_list", "bqsr_prep", "bqsr_apply", "adapt") if k in st), flush=True)
 ''' % ROOT
