@@ -73,3 +73,13 @@ def test_c_client_runs_the_path(tmp_path):
     assert lines[0] == "order 2 0 1 3 flags 16 0 1024 4", out.stdout
     assert lines[1] == "libA unpaired 3 dups 1 unmapped 1"
     assert lines[2] == "apply-before-finalize rc -16"
+
+
+def test_header_is_valid_c_and_cxx(tmp_path):
+    """include/elprep_b200.h compiles on its own as C99 and as C++17 (extern "C" guards), with all warnings on"""
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    (tmp_path / "t.c").write_text('#include "elprep_b200.h"\nint main(void) { elp_config c; elp_batch b; elp_dup_metrics m; (void)c; (void)b; (void)m; return ELP_OK; }\n')
+    (tmp_path / "t.cpp").write_text('#include "elprep_b200.h"\nint main() { elp_ctx* x = nullptr; return elp_n_reads(x) == 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", inc, "-c", str(tmp_path / "t.c"), "-o", str(tmp_path / "t.o")])
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", inc, "-c", str(tmp_path / "t.cpp"), "-o", str(tmp_path / "t2.o")])
