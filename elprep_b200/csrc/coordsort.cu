@@ -142,16 +142,31 @@ struct GatherCols {
     uint64_t *s_qual_off, *s_seq_off, *s_cigar_off; uint32_t* s_ncigar;
 };
 
-__global__ void __launch_bounds__(256) gather_cols_kernel(uint64_t n, const uint32_t* __restrict__ perm, GatherCols g) {
+// The fixed-width columns of a read packed into one 64-byte row (streaming pass, coalesced), so that the permuted gather below
+// touches two sectors per read instead of eleven:
+//   u32[0..5] refid pos nref pnext tlen rg   [6] lseq  [7] ncigar  [8,9] qual_off  [10,11] seq_off  [12,13] cigar_off  [14] mapq
+__global__ void __launch_bounds__(256) pack_rows_kernel(uint64_t n, GatherCols g, uint4* __restrict__ rows) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t q0 = g.qual_off[i], q1 = g.qual_off[i + 1], c0 = g.cigar_off[i], c1 = g.cigar_off[i + 1], s0 = g.seq_off[i];
+    uint4* r = rows + 4 * i;
+    r[0] = make_uint4((uint32_t)g.refid[i], (uint32_t)g.pos[i], (uint32_t)g.nref[i], (uint32_t)g.pnext[i]);
+    r[1] = make_uint4((uint32_t)g.tlen[i], (uint32_t)g.rg[i], (uint32_t)(q1 - q0), (uint32_t)(c1 - c0));
+    r[2] = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)s0, (uint32_t)(s0 >> 32));
+    r[3] = make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)g.mapq[i], 0u);
+}
+
+__global__ void __launch_bounds__(256) gather_cols_kernel(uint64_t n, const uint32_t* __restrict__ perm, GatherCols g, const uint4* __restrict__ rows) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t i = perm[k];
-    g.s_refid[k] = g.refid[i]; g.s_pos[k] = g.pos[i]; g.s_nref[k] = g.nref[i]; g.s_pnext[k] = g.pnext[i]; g.s_tlen[k] = g.tlen[i]; g.s_rg[k] = g.rg[i];
-    g.s_flag[k] = g.flag[i]; g.s_mapq[k] = g.mapq[i];
-    const uint64_t q0 = g.qual_off[i], q1 = g.qual_off[i + 1];
-    g.s_qual_off[k] = q0; g.s_lseq[k] = (int32_t)(q1 - q0); g.s_seq_off[k] = g.seq_off[i];
-    const uint64_t c0 = g.cigar_off[i], c1 = g.cigar_off[i + 1];
-    g.s_cigar_off[k] = c0; g.s_ncigar[k] = (uint32_t)(c1 - c0);
+    const uint4* r = rows + 4 * (uint64_t)i;
+    const uint4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), d = __ldg(r + 3);
+    g.s_refid[k] = (int32_t)a.x; g.s_pos[k] = (int32_t)a.y; g.s_nref[k] = (int32_t)a.z; g.s_pnext[k] = (int32_t)a.w; g.s_tlen[k] = (int32_t)b.x; g.s_rg[k] = (int32_t)b.y;
+    g.s_flag[k] = g.flag[i];                       // FLAG from the column: duplicate marking set bits after the rows were packed
+    g.s_mapq[k] = (uint8_t)d.z;
+    g.s_qual_off[k] = ((uint64_t)c.y << 32) | c.x; g.s_lseq[k] = (int32_t)b.z; g.s_seq_off[k] = ((uint64_t)c.w << 32) | c.z;
+    g.s_cigar_off[k] = ((uint64_t)d.y << 32) | d.x; g.s_ncigar[k] = b.w;
 }
 
 __global__ void __launch_bounds__(256) lseq_u32_kernel(uint64_t n, const int32_t* __restrict__ lseq, uint32_t* __restrict__ out) {
@@ -263,8 +278,14 @@ int phase_coordinate_sort(elp_ctx* c, int order) {   // 0 keep, 1 coordinate, 2 
         GatherCols g{c->refid.p, c->pos.p, c->nref.p, c->pnext.p, c->tlen.p, c->rg.p, c->flag.p, c->mapq.p, c->qual_off.p, c->seq_off.p, c->cigar_off.p,
                      c->s_refid.p, c->s_pos.p, c->s_nref.p, c->s_pnext.p, c->s_tlen.p, c->s_rg.p, c->s_lseq.p, c->s_flag.p, c->s_mapq.p,
                      c->s_qual_off.p, c->s_seq_off.p, c->s_cigar_off.p, c->s_ncigar.p};
+        // rows live in the key scratch (free here): 4 x uint4 per read
+        CUDA_TRY(c, c->keys_a.reserve(8 * n + 8, c->stream));
+        uint4* rows = reinterpret_cast<uint4*>(c->keys_a.p);
+        c->begin("pack_rows", (double)n * (27 + 24 + 64));
+        pack_rows_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, g, rows);
+        c->end(); LAUNCH_CHECK(c);
         c->begin("gather_cols", (double)n * (4 + 27 + 24 + 27 + 28 + 8));
-        gather_cols_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->perm.p, g);
+        gather_cols_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->perm.p, g, rows);
         c->end(); LAUNCH_CHECK(c);
         CUDA_TRY(c, c->scan_tmp.reserve(n + 4, c->stream));
         lseq_u32_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->s_lseq.p, c->scan_tmp.p);
