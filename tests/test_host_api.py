@@ -60,3 +60,26 @@ def test_simple_filters_as_column_predicates():
     assert names(filters.RemoveMappingQualityLessThan(30)(h)(b)) == ["a", "e"] and filters.RemoveMappingQualityLessThan(0) is None
     assert names(filters.RemoveDuplicateReads(h)(b)) == ["a", "b", "c", "e"]
     assert filters.RemoveUnmappedReads(h)(b.take([0, 3])) .n == 2
+
+
+def test_spread_exchange_degenerate_cases():
+    """elprep_b200.multi with one worker (nothing to exchange) and with a batch that has no cross-group pairs"""
+    from elprep_b200 import multi, synth
+    contigs = [("c1", 200_000), ("c2", 100_000)]
+    w = synth.make_workload(500, contigs, seed=5, cross_contig_frac=0.0, want_reference=False)
+    calls = []
+
+    def md(batch, header):
+        calls.append(batch.n)
+        return batch.flag.copy(), None
+    owner1 = multi.owner_table(w.header, multi.contig_groups(contigs, 1))
+    before = w.batch.flag.copy()
+    assert multi.exchange_spread_duplicates(w.batch, w.header, owner1, 0, 1, md, lambda o: [o]) is None
+    assert np.array_equal(before, w.batch.flag) and calls == []
+    owner2 = multi.owner_table(w.header, multi.contig_groups(contigs, 2))
+    assert sorted(set(owner2.tolist())) == [0, 1]
+    idx, powner = multi.spread_reads(w.batch, owner2, 0)
+    assert idx.size == 0 and powner.size == 0
+    own = [multi.partition(w.batch, owner2, r, 2) for r in range(2)]
+    assert sorted(np.concatenate(own).tolist()) == list(range(w.batch.n))          # every read has exactly one owner
+    assert bool((w.batch.refid[own[1]] < 0).sum() == (w.batch.refid < 0).sum())       # unmapped reads go to the last rank
