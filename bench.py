@@ -113,6 +113,36 @@ def cpu_pipeline(w, n_reads, threads):
     return b.n, (t1 - t0) + (t4 - t3)
 
 
+def verify_against_oracle(ctx, w, out_np, n_reads, threads):
+    """untimed: the output of the LAST timed step (still in the pinned fetch buffers and in the context) against the oracle run on
+    the same reads: output permutation, FLAG of every record, BQSR table counters, EmpiricalQuality, every QUAL byte"""
+    import hashlib
+    import oracle
+    from elprep_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import oracle_tables_dense
+    t0 = time.time()
+    idx, flag, qoff, qual = out_np
+    g_tables, g_emp = ctx.tables_get(), ctx.empirical_get()
+    b = w.batch                                   # in place: the timed steps are over
+    oracle.mark_duplicates(b, w.header, n_threads=threads)
+    perm = oracle.coordinate_sort(b, n_threads=threads)
+    srt = synth.take(b, perm, threads=threads)
+    ref = oracle.Reference(w.header, w.contig_bases, w.sites)
+    tb = oracle.bqsr_gather(srt, w.header, ref, n_threads=threads)
+    oracle.bqsr_finalize(tb)
+    oracle.bqsr_apply(srt, w.header, tb, n_threads=threads)
+    o_tables, o_emp = oracle_tables_dense(tb)
+    nq = int(qoff[n_reads])
+    checks = {"order": bool(np.array_equal(idx[:n_reads], perm.astype(np.uint64))), "flag": bool(np.array_equal(flag[:n_reads], srt.flag)),
+              "tables": bool(np.array_equal(g_tables, o_tables)), "empirical_quality": bool(np.array_equal(g_emp, o_emp)),
+              "qual": bool(nq == srt.qual.size and np.array_equal(qual[:nq], srt.qual))}
+    return {"ok": all(checks.values()), "checks": checks, "reads": int(n_reads), "duplicates": int(((flag[:n_reads] & 0x400) != 0).sum()),
+            "observations": int(g_tables[:, :, 0, 0].sum()), "mismatches": int(g_tables[:, :, 0, 1].sum()),
+            "flag_sha256": hashlib.sha256(flag[:n_reads].tobytes()).hexdigest()[:16], "qual_sha256": hashlib.sha256(qual[:nq].tobytes()).hexdigest()[:16],
+            "against": "oracle/ (C restatement of the reference) on the same reads", "seconds": round(time.time() - t0, 1)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -122,6 +152,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--verify", dest="verify", action="store_true", default=None, help="check the last step's output against the oracle (default: on at --gpus 1)")
+    ap.add_argument("--no-verify", dest="verify", action="store_false")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     from elprep_b200 import synth
@@ -257,6 +289,9 @@ def main():
                 "launches": k["launches"], "avg_launch_ms": k["ms"] / max(1, k["launches"]), "alg_bytes_per_launch": k["alg_bytes"] / max(1, k["launches"])}
     kern = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                 "GBps": (v["alg_bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["alg_bytes"] > 0 else None} for n, v in sorted(stats.items(), key=lambda kv: -kv[1]["ms"])}
+    verified = None
+    if args.verify if args.verify is not None else world == 1:
+        verified = verify_against_oracle(ctx, w, out_np, n_reads, threads)
     cpu = None
     if not args.no_cpu_baseline:
         n_s, t_s = cpu_pipeline(w, args.cpu_sample, threads)
@@ -266,7 +301,7 @@ def main():
             "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
             "config": {"workload": workload_name, "reads_per_gpu": n_reads, "parallelism": f"contig-group x{world}", "flush": "inputs >> L2 (re-ingested every step)"},
             "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps},
-            "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": kern}
+            "gpu_launches": launches, "verified": (verified or {}).get("ok"), "verify": verified, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": kern}
     print(json.dumps(line))
     if dist:
         dist.barrier(); dist.destroy_process_group()

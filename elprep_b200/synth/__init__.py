@@ -123,3 +123,30 @@ def encode_bam(batch, header, threads=8):
     out = np.empty(int(rec_off[-1]), dtype=np.uint8)
     L.synth_encode_bam(C.c_int64(n), *ptr, rec_off.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), C.c_int32(threads))
     return out, rec_off
+
+
+def take(batch, idx, threads=None):
+    """``batch.take(idx)`` with the ragged gathers done by host threads (no element-wise index arrays): what the bench's
+    verification and the C1/C2-sized parity tests use to materialise the oracle's output order."""
+    lib = _L()
+    threads = threads or min(32, os.cpu_count() or 1)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    n = idx.shape[0]
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+
+    def ragged(off, data):
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        lens = (off[1:] - off[:-1])[idx]
+        no = np.zeros(n + 1, dtype=np.uint64)
+        np.cumsum(lens, out=no[1:])
+        out = np.empty(int(no[-1]), dtype=data.dtype)
+        if n:
+            lib.synth_take_ragged(vp(idx), C.c_int64(n), vp(off), vp(data), C.c_int32(data.dtype.itemsize), vp(no), vp(out), C.c_int32(threads))
+        return no, out
+    qo, qn = ragged(batch.qname_off, batch.qname)
+    co, cg = ragged(batch.cigar_off, batch.cigar)
+    _, sq = ragged(batch.seq_off, batch.seq)
+    _, ql = ragged(batch.qual_off, batch.qual)
+    return sam.AlignmentBatch(refid=batch.refid[idx], pos=batch.pos[idx], flag=batch.flag[idx], mapq=batch.mapq[idx], nref=batch.nref[idx],
+                              pnext=batch.pnext[idx], tlen=batch.tlen[idx], rg=batch.rg[idx], qname_off=qo, qname=qn, cigar_off=co, cigar=cg,
+                              lseq=batch.lseq[idx], seq=sq, qual=ql)

@@ -346,4 +346,15 @@ int synth_encode_bam(int64_t n, const int32_t* refid, const int32_t* pos, const 
     });
     return 0;
 }
+// out[out_off[k] .. out_off[k+1]) = data[off[idx[k]] .. off[idx[k]+1])  (elem bytes per element): the ragged gather behind
+// AlignmentBatch.take at bench scale (30 M reads), where numpy index arrays would not fit in host memory
+int synth_take_ragged(const int64_t* idx, int64_t n, const uint64_t* off, const uint8_t* data, int32_t elem, const uint64_t* out_off, uint8_t* out, int32_t threads) {
+    par_for(n, threads, [&](int64_t lo, int64_t hi, int) {
+        for (int64_t k = lo; k < hi; k++) {
+            const uint64_t a = off[idx[k]], b = off[idx[k] + 1];
+            std::memcpy(out + out_off[k] * (uint64_t)elem, data + a * (uint64_t)elem, (size_t)((b - a) * (uint64_t)elem));
+        }
+    });
+    return 0;
+}
 }
