@@ -46,8 +46,10 @@ __global__ void __launch_bounds__(256) bam_fixed_kernel(BamArgs A) {
     const int32_t refid = (int32_t)rd32(r + 4), pos = (int32_t)rd32(r + 8);
     const uint32_t l_name = r[12], mapq = r[13], n_cig = rd16(r + 16), flag = rd16(r + 18);
     const int32_t l_seq = (int32_t)rd32(r + 20), nref = (int32_t)rd32(r + 24), pnext = (int32_t)rd32(r + 28), tlen = (int32_t)rd32(r + 32);
-    const uint64_t var = (uint64_t)l_name + 4ull * n_cig + (uint64_t)((l_seq + 1) >> 1) + (uint64_t)max(l_seq, 0);
-    if (l_name < 1 || l_seq < 0 || BAM_FIXED + var > rec_len || refid >= A.n_contigs || nref >= A.n_contigs) bad = 1;
+    // all lengths in 64 bits: a crafted l_seq near INT_MAX must not wrap (l_seq > rec_len is malformed whatever else the record says)
+    const uint64_t lsq = l_seq < 0 ? 0ull : (uint64_t)(uint32_t)l_seq;
+    const uint64_t var = (uint64_t)l_name + 4ull * n_cig + ((lsq + 1) >> 1) + lsq;
+    if (l_name < 1 || l_seq < 0 || lsq > rec_len || BAM_FIXED + var > rec_len || refid >= A.n_contigs || nref >= A.n_contigs) bad = 1;
     const uint64_t k = A.n0 + i;
     A.refid[k] = refid < 0 ? -1 : refid; A.pos[k] = pos + 1; A.flag[k] = (uint16_t)flag; A.mapq[k] = (uint8_t)mapq;
     A.nref[k] = nref < 0 ? -1 : nref; A.pnext[k] = pnext + 1; A.tlen[k] = tlen;
@@ -70,6 +72,7 @@ __global__ void __launch_bounds__(256) bam_fixed_kernel(BamArgs A) {
                     const uint64_t es = (sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : ((sub == 'i' || sub == 'I' || sub == 'f') ? 4 : 0));
                     if (!es) bad = 1;
                     if (t0 == 'C' && t1 == 'G') bad = 2;     // long-CIGAR convention: not supported here
+                    if (cnt * es > rec_len) { bad = 1; break; }    // (cnt < 2^32, es <= 4: no overflow; bounded before it is added to x)
                     sz = 5 + cnt * es; break;
                 }
                 default: bad = 1;

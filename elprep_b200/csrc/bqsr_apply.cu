@@ -16,6 +16,7 @@
 // With lut == nullptr the kernel only materialises the output-order QUAL stream (no BQSR requested).
 #include "ctx.h"
 #include "bqsr_simd.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -191,5 +192,10 @@ int run_apply_kernel(elp_ctx* c, bool with_lut) {
 int phase_bqsr_apply(elp_ctx* c) {
     if (!c->sorted) return c->fail(E_STATE, "elp_bqsr_apply called before elp_sort_markdup");
     if (!c->finalized) return c->fail(E_STATE, "elp_bqsr_apply called before elp_bqsr_finalize");
+    // the look-up table must cover every cycle of the reads now loaded (it was sized by elp_bqsr_finalize, possibly before they arrived)
+    int rc = phase_adapt(c);
+    if (rc) return rc;
+    const int need = std::max(1, std::min(c->max_cycle, std::max(c->h_ranges.lseq_max, 1)));
+    if (c->lut_maxcyc < need) { rc = build_apply_lut(c, need); if (rc) return rc; }
     return run_apply_kernel(c, true);
 }

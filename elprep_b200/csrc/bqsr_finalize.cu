@@ -236,6 +236,8 @@ template <class F> void host_parallel_for(int n, F f) {
 
 }  // namespace
 
+int build_apply_lut(elp_ctx* c, int Lc);
+
 int phase_bqsr_finalize(elp_ctx* c, const char* report_path) {
     if (!c->gathered) return c->fail(E_STATE, "elp_bqsr_finalize called before elp_bqsr_gather / elp_bqsr_tables_put");
     const TableGeom& g = c->geom;
@@ -257,12 +259,24 @@ int phase_bqsr_finalize(elp_ctx* c, const char* report_path) {
     for (int cv = 0; cv < g.n_cov; cv++) comb[cv] = combine(T, cv);
     if (report_path) { int rc = write_report(c, T, c->h_emp, comb, report_path); if (rc) return rc; }
 
-    // ---- the apply look-up table (ApplyBQSR :936-1006) ----
+    c->finalized = true;
+    // the apply look-up table covers the cycles of the reads loaded so far; elp_bqsr_apply rebuilds it if longer reads arrive
+    // later (apply-only workers: tables_put -> finalize -> append -> sort -> apply)
+    if (c->n) { int rc = phase_adapt(c); if (rc) return rc; }
+    return build_apply_lut(c, std::max(1, std::min(c->max_cycle, std::max(c->h_ranges.lseq_max, 1))));
+}
+
+// ---- the apply look-up table (ApplyBQSR :936-1006): recalibrated QUAL for (covariate, QUAL, cycle in [-Lc, Lc], context) ----
+int build_apply_lut(elp_ctx* c, int Lc) {
+    if (!c->finalized) return c->fail(E_STATE, "apply look-up table requested before elp_bqsr_finalize");
+    const TableGeom& g = c->geom;
+    Tables T{g, c->h_tables.data()};
+    std::vector<Combined> comb(g.n_cov);
+    for (int cv = 0; cv < g.n_cov; cv++) comb[cv] = combine(T, cv);
     std::vector<int64_t> qmap; std::vector<uint8_t> quant;
     quantized(T, c->h_emp, c->quantize_levels, qmap, quant);
     std::vector<uint8_t> stat; const bool have_stat = !c->sqq.empty();
     if (have_stat) stat = static_quantized(c->sqq);
-    const int Lc = std::max(1, std::min(c->max_cycle, std::max(c->h_ranges.lseq_max, 1)));
     const int ncyc = 2 * Lc + 1;
     std::vector<uint8_t> lut((size_t)g.n_cov * 94 * ncyc * 17, 0);
     std::vector<uint8_t> cov_exists(g.n_cov, 0);
@@ -309,6 +323,5 @@ int phase_bqsr_finalize(elp_ctx* c, const char* report_path) {
     CUDA_TRY(c, cudaMemcpyAsync(c->d_cov_exists, cov_exists.data(), g.n_cov, cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->lut_maxcyc = Lc;
-    c->finalized = true;
     return E_OK;
 }

@@ -206,6 +206,7 @@ int phase_coordinate_sort(elp_ctx* c, int order);   // 0 keep, 1 coordinate, 2 q
 int phase_bqsr_gather(elp_ctx* c);
 int phase_bqsr_finalize(elp_ctx* c, const char* report_path);
 int phase_bqsr_apply(elp_ctx* c);
+int build_apply_lut(elp_ctx* c, int Lc);   // bqsr_finalize.cu
 int upload_side_inputs(elp_ctx* c);
 int pack_reference(elp_ctx* c, int contig);
 int check_device_errors(elp_ctx* c);

@@ -47,8 +47,7 @@ int radix_sort_impl(elp_ctx* c, K* ka, K* kb, uint32_t* va, uint32_t* vb, uint64
     if ((reinterpret_cast<uintptr_t>(va) | reinterpret_cast<uintptr_t>(vb)) & 15) return c->fail(E_INVAL, "radix sort: payload buffers must be 16-byte aligned");
     auto kern = rs_onesweep_kernel<K, Cfg<K>::THREADS, Cfg<K>::ITEMS, Cfg<K>::MIN_CTAS>;
     const size_t smem = smem_bytes<K>();
-    static bool attr_set = false;   // per template instantiation
-    if (!attr_set) { CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    CUDA_TRY(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: set on every call (cheap)
     nm = std::string("radix_onesweep_") + tag;
     K* in = ka; K* out = kb; uint32_t* vin = va; uint32_t* vout = vb;
     for (int p = 0; p < plan.n_passes; p++) {
