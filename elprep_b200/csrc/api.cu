@@ -36,6 +36,35 @@ __global__ void __launch_bounds__(256) rel_off_kernel(uint64_t n, const uint64_t
     if (i <= n) out[i] = off[first + i] - off[first];
 }
 
+// which QUAL values occur (bit q of a 128-bit map): the BQSR count kernel classifies QUAL bytes through an 8-entry table and is only
+// selected when that table separates every value that is present.  Runs at ingest over the bytes just appended.
+__global__ void __launch_bounds__(256) qual_presence_kernel(const uint8_t* __restrict__ q, uint64_t n, uint32_t* __restrict__ present) {
+    unsigned long long lo = 0, hi = 0;
+    uint32_t other = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t head = (16 - (reinterpret_cast<uintptr_t>(q) & 15)) & 15;             // bytes before the first aligned 16-byte chunk
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto one = [&](uint32_t v) { lo |= 1ull << v; hi |= 1ull << (v - 64u); other |= v & 0x80u; };   // shifts >= 64 give 0
+    if (t < head && t < n) one(q[t]);
+    const uint64_t n16 = n > head ? (n - head) >> 4 : 0;
+    const uint4* q4 = reinterpret_cast<const uint4*>(q + head);
+    for (uint64_t i = t; i < n16; i += stride) {
+        const uint4 v = ld_stream_u4(q4 + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) { one(w[k] & 255u); one((w[k] >> 8) & 255u); one((w[k] >> 16) & 255u); one(w[k] >> 24); }
+    }
+    const uint64_t tail0 = head + (n16 << 4);
+    if (tail0 + t < n && t < 16) one(q[tail0 + t]);
+    for (int o = 16; o; o >>= 1) { lo |= __shfl_xor_sync(FULL_MASK, lo, o); hi |= __shfl_xor_sync(FULL_MASK, hi, o); other |= __shfl_xor_sync(FULL_MASK, other, o); }
+    if ((threadIdx.x & 31) == 0) {
+        if ((uint32_t)lo) atomicOr(present, (uint32_t)lo);
+        if ((uint32_t)(lo >> 32)) atomicOr(present + 1, (uint32_t)(lo >> 32));
+        if ((uint32_t)hi) atomicOr(present + 2, (uint32_t)hi);
+        if ((uint32_t)(hi >> 32) || other) atomicOr(present + 3, (uint32_t)(hi >> 32) | (other ? 0x80000000u : 0u));   // bit 127: some byte >= 128
+    }
+}
+
 template <class T> int grow(elp_ctx* c, DBuf<T>& b, size_t need, size_t keep) {
     cudaError_t e = b.reserve(need, c->stream, keep);
     if (e != cudaSuccess) return c->fail(e == cudaErrorMemoryAllocation ? E_NOMEM : E_CUDA, "device allocation of %zu bytes failed: %s", need * sizeof(T), cudaGetErrorString(e));
@@ -45,14 +74,24 @@ template <class T> int grow(elp_ctx* c, DBuf<T>& b, size_t need, size_t keep) {
 
 }  // namespace
 
+int qual_presence_update(elp_ctx* c, uint64_t first_byte, uint64_t n_bytes) {
+    if (!n_bytes) return E_OK;
+    const unsigned grid = (unsigned)std::min<uint64_t>((n_bytes / 16 + 255) / 256 + 1, 148 * 16);
+    c->launches++;
+    qual_presence_kernel<<<grid, 256, 0, c->stream>>>(c->qual.p + first_byte, n_bytes, c->d_qpresent);
+    LAUNCH_CHECK(c);
+    return E_OK;
+}
+
 int upload_side_inputs(elp_ctx* c) {
     if (!c->side_dirty) return E_OK;
     const int nc = c->n_contigs;
-    std::vector<const uint8_t*> rp(nc), np(nc); std::vector<const int32_t*> sp(nc);
-    for (int i = 0; i < nc; i++) { rp[i] = c->d_ref[i]; np[i] = c->d_refnib_raw[i] ? c->d_refnib_raw[i] + 32 : nullptr; sp[i] = c->d_sites[i]; }
+    std::vector<const uint8_t*> rp(nc), np(nc), hp(nc); std::vector<const int32_t*> sp(nc);
+    for (int i = 0; i < nc; i++) { rp[i] = c->d_ref[i]; np[i] = c->d_refnib_raw[i] ? c->d_refnib_raw[i] + 32 : nullptr; hp[i] = c->d_refhot_raw[i] ? c->d_refhot_raw[i] + REFHOT_PAD : nullptr; sp[i] = c->d_sites[i]; }
     if (nc) {
         CUDA_TRY(c, cudaMemcpyAsync(c->d_ref_ptrs, rp.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_refnib_ptrs, np.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(c->d_refhot_ptrs, hp.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_ref_len, c->ref_len.data(), nc * 8, cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_site_ptrs, sp.data(), nc * sizeof(void*), cudaMemcpyHostToDevice, c->stream));
         CUDA_TRY(c, cudaMemcpyAsync(c->d_n_sites, c->n_sites.data(), nc * 8, cudaMemcpyHostToDevice, c->stream));
@@ -107,15 +146,18 @@ int elp_create(const elp_config* cfg, elp_ctx** out) {
     const int nc = std::max(1, c->n_contigs), nr = std::max(1, c->n_rg);
     bool ok = cudaMalloc(&c->d_rg_lib, nr * 4) == cudaSuccess && cudaMalloc(&c->d_rg_cov, nr * 4) == cudaSuccess && cudaMalloc(&c->d_contig_len, nc * 4) == cudaSuccess &&
               cudaMalloc(&c->d_ranges, sizeof(DeviceRanges)) == cudaSuccess && cudaMalloc(&c->d_err, 4) == cudaSuccess &&
-              cudaMalloc(&c->d_ref_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_refnib_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_ref_len, nc * 8) == cudaSuccess &&
+              cudaMalloc(&c->d_ref_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_refnib_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_refhot_ptrs, nc * sizeof(void*)) == cudaSuccess &&
+              cudaMalloc(&c->d_bq_small, 512 * 4) == cudaSuccess && cudaMalloc(&c->d_qpresent, 16) == cudaSuccess && cudaMalloc(&c->d_ref_len, nc * 8) == cudaSuccess &&
               cudaMalloc(&c->d_site_ptrs, nc * sizeof(void*)) == cudaSuccess && cudaMalloc(&c->d_n_sites, nc * 8) == cudaSuccess &&
               cudaMalloc(&c->d_tables, std::max<size_t>(16, c->geom.cells() * 2 * sizeof(int64_t))) == cudaSuccess;
     if (!ok) { c->err = "device allocation failed in elp_create"; return bail(ELP_ENOMEM); }
     if (c->n_rg) { cudaMemcpy(c->d_rg_lib, c->rg_lib.data(), c->n_rg * 4, cudaMemcpyHostToDevice); cudaMemcpy(c->d_rg_cov, c->rg_cov.data(), c->n_rg * 4, cudaMemcpyHostToDevice); }
     if (c->n_contigs) cudaMemcpy(c->d_contig_len, c->contig_len.data(), c->n_contigs * 4, cudaMemcpyHostToDevice);
     cudaMemset(c->d_err, 0, 4);
+    cudaMemset(c->d_qpresent, 0, 16);
+    c->n_qual = c->n_seq = ARENA_FRONT_PAD;
     cudaMemset(c->d_tables, 0, std::max<size_t>(16, c->geom.cells() * 2 * sizeof(int64_t)));
-    c->d_ref.assign(c->n_contigs, nullptr); c->d_refnib_raw.assign(c->n_contigs, nullptr); c->ref_len.assign(c->n_contigs, 0);
+    c->d_ref.assign(c->n_contigs, nullptr); c->d_refnib_raw.assign(c->n_contigs, nullptr); c->d_refhot_raw.assign(c->n_contigs, nullptr); c->ref_len.assign(c->n_contigs, 0);
     c->d_sites.assign(c->n_contigs, nullptr); c->n_sites.assign(c->n_contigs, 0);
     if ((e = cudaGetLastError()) != cudaSuccess) { c->err = std::string("elp_create: ") + cudaGetErrorString(e); return bail(ELP_ECUDA); }
     *out = c;
@@ -128,14 +170,15 @@ void elp_destroy(elp_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto p : c->d_ref) if (p) cudaFree(p);
     for (auto p : c->d_refnib_raw) if (p) cudaFree(p);
+    for (auto p : c->d_refhot_raw) if (p) cudaFree(p);
     for (auto p : c->d_sites) if (p) cudaFree(p);
-    void* singles[] = {c->d_rg_lib, c->d_rg_cov, c->d_contig_len, c->d_ranges, c->d_err, (void*)c->d_ref_ptrs, (void*)c->d_refnib_ptrs, c->d_ref_len, (void*)c->d_site_ptrs, c->d_n_sites, c->d_tables,
+    void* singles[] = {c->d_rg_lib, c->d_rg_cov, c->d_contig_len, c->d_ranges, c->d_err, (void*)c->d_ref_ptrs, (void*)c->d_refnib_ptrs, (void*)c->d_refhot_ptrs, c->d_bq_small, c->d_qpresent, c->d_ref_len, (void*)c->d_site_ptrs, c->d_n_sites, c->d_tables,
                        c->d_lut, c->d_cov_exists, c->d_opt_ctr, c->d_opt_hist, c->d_opt_ovf, c->d_opt_small, c->d_rg_names, c->d_rg_name_off, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
     for (void* p : singles) if (p) cudaFree(p);
     c->refid.release(); c->pos.release(); c->nref.release(); c->pnext.release(); c->tlen.release(); c->rg.release(); c->flag.release(); c->mapq.release();
     c->qname_off.release(); c->cigar_off.release(); c->qual_off.release(); c->seq_off.release(); c->qname.release(); c->seq.release(); c->qual.release(); c->cigar.release();
     c->bam_raw.release(); c->bam_off.release(); c->bam_all.release(); c->bam_all_off.release(); c->bam_start.release(); c->lseq_stage.release(); c->off_stage.release(); c->upos.release(); c->score.release(); c->qhash.release(); c->keys_a.release(); c->keys_b.release();
-    c->vals_a.release(); c->vals_b.release(); c->mate.release(); c->pair_a.release(); c->pair_b.release(); c->scan_tmp.release(); c->scan_blk.release(); c->bytes_tmp.release();
+    c->bq_recs.release(); c->bq_segs.release(); c->vals_a.release(); c->vals_b.release(); c->mate.release(); c->pair_a.release(); c->pair_b.release(); c->scan_tmp.release(); c->scan_blk.release(); c->bytes_tmp.release();
     c->perm.release(); c->s_refid.release(); c->s_pos.release(); c->s_nref.release(); c->s_pnext.release(); c->s_tlen.release(); c->s_rg.release(); c->s_lseq.release();
     c->s_flag.release(); c->s_mapq.release(); c->s_qual_off.release(); c->s_seq_off.release(); c->s_cigar_off.release(); c->s_out_off.release(); c->s_ncigar.release(); c->qual_out.release();
     for (auto& pe : c->pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
@@ -149,7 +192,8 @@ int elp_reset(elp_ctx* c) {
     if (!c) return ELP_EINVAL;
     cudaSetDevice(c->device);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    c->n = c->n_qname = c->n_cigar = c->n_qual = c->n_seq = 0; c->n_bam = c->bam_reads = 0; c->n_filtered = 0;
+    c->n = c->n_qname = c->n_cigar = 0; c->n_qual = c->n_seq = ARENA_FRONT_PAD; c->n_bam = c->bam_reads = 0; c->n_filtered = 0;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_qpresent, 0, 16, c->stream));
     c->adapted = c->sorted = c->qual_out_valid = c->gathered = c->finalized = c->opt_valid = false;
     c->launches = 0;
     CUDA_TRY(c, cudaMemsetAsync(c->d_err, 0, 4, c->stream));
@@ -165,7 +209,7 @@ int elp_reserve(elp_ctx* c, uint64_t n_reads, uint64_t n_bases, uint64_t n_cigar
     TRY(grow(c, c->rg, n, c->n)); TRY(grow(c, c->flag, n + 1, c->n)); TRY(grow(c, c->mapq, n, c->n));
     TRY(grow(c, c->qname_off, n + 1, c->n + 1)); TRY(grow(c, c->cigar_off, n + 1, c->n + 1)); TRY(grow(c, c->qual_off, n + 1, c->n + 1)); TRY(grow(c, c->seq_off, n + 1, c->n + 1));
     TRY(grow(c, c->qname, n_qname_bytes + 64, c->n_qname)); TRY(grow(c, c->cigar, n_cigar_ops + 16, c->n_cigar));
-    TRY(grow(c, c->qual, n_bases + 64, c->n_qual)); TRY(grow(c, c->seq, n_bases / 2 + n_reads + 64, c->n_seq));
+    TRY(grow(c, c->qual, n_bases + 64 + ARENA_FRONT_PAD, c->n_qual)); TRY(grow(c, c->seq, n_bases / 2 + n_reads + 64 + ARENA_FRONT_PAD, c->n_seq));
     return ELP_OK;
 }
 
@@ -250,6 +294,7 @@ int elp_append_batch(elp_ctx* c, const elp_batch* b) {
     LAUNCH_CHECK(c);
     TRY(exclusive_scan_u32_to_u64(c, qlen, c->qual_off.p + n0, bn));
     if (c->n_qual) { add_base_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->qual_off.p + n0, c->n_qual); c->launches++; }
+    TRY(qual_presence_update(c, c->n_qual, bbases));
     TRY(exclusive_scan_u32_to_u64(c, slen, c->seq_off.p + n0, bn));
     if (c->n_seq) { add_base_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->seq_off.p + n0, c->n_seq); c->launches++; }
     LAUNCH_CHECK(c);

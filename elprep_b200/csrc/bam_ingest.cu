@@ -295,6 +295,7 @@ extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_byt
     c->begin("bam_copy", 2.0 * (double)n_bytes);
     bam_copy_kernel<<<nblk(bn * 32, 256), 256, 0, s>>>(B);
     c->end(); LAUNCH_CHECK(c);
+    TRY(qual_presence_update(c, c->n_qual, ends[3] - c->n_qual));
     CUDA_TRY(c, cudaStreamSynchronize(s));   // the caller's buffer may be released after return (cgo pointer rules)
     // keep the raw records for elp_fetch_bam (only meaningful while every read of the context came in as BAM)
     if (c->bam_reads == n0) {

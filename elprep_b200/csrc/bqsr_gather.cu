@@ -18,6 +18,7 @@
 #include <vector>
 #include "ctx.h"
 #include "bqsr_simd.cuh"
+#include "bqsr_lane.cuh"
 
 namespace {
 
@@ -190,12 +191,14 @@ struct GatherArgs {
     // shared-memory privatisation: observation counters of the frequent QUAL values live in shared memory
     int8_t qslot[94]; uint8_t slot_q[94]; int n_slots, Lc;
     int ncols_s, ctx_col_s;          // chunk kernel rows: skewed cycle cells [0, ctx_col_s), then 16 context cells
+    const uint32_t* in_list; uint32_t n_in;   // when set: only these reads (the general path behind bqsr_prep2_kernel); they all go through the per-lane CIGAR walk
 };
 
 // ---------------------------------------------------------------- kernel A: one thread per read
 __global__ void __launch_bounds__(128) bqsr_prep_kernel(GatherArgs A) {
-    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= A.n) return;
+    const uint64_t tix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tix >= (A.in_list ? (uint64_t)A.n_in : A.n)) return;
+    const uint64_t k = A.in_list ? (uint64_t)A.in_list[tix] : tix;
     ReadDesc d; d.qloc = 0; d.nloc = 0; d.c_pos = 0; d.c_s0 = 0; d.c_len = 0; d.flags = 0; d.cov = 0; d.n_skip = 0; d.pad = 0; d.ovf = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++) { d.skip[r][0] = 0; d.skip[r][1] = 0; }
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(128) bqsr_prep_kernel(GatherArgs A) {
         }
     }
     // chunk kernel: one M run, every cycle inside --max-cycle (|cycle| <= L), inside the contig, fits the lanes of a read
-    if ((d.flags & DF_SINGLE_M) && !(d.flags & DF_SKIP_OVF) && L <= A.geom.max_cycle && L <= CHUNK * A.lanes_per_read &&
+    if (!A.in_list && (d.flags & DF_SINGLE_M) && !(d.flags & DF_SKIP_OVF) && L <= A.geom.max_cycle && L <= CHUNK * A.lanes_per_read &&
         (uint64_t)(a.pos - 1) + (uint64_t)L <= A.ref_len[refid]) d.flags |= DF_LEAN;
     else if (!(d.flags & DF_SKIP_OVF) && L <= A.geom.max_cycle && L <= CHUNK * A.lanes_per_read) d.flags |= DF_CHUNKG;
     done();
@@ -565,9 +568,11 @@ __global__ void __launch_bounds__(256) gen_list_kernel(GatherArgs A) {
     __shared__ uint32_t s_cnt[2], s_base[2];
     if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
     __syncthreads();
-    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t tix = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = tix < (A.in_list ? (uint64_t)A.n_in : A.n);
+    const uint64_t k = in ? (A.in_list ? (uint64_t)A.in_list[tix] : tix) : 0;
     int which = -1;
-    if (k < A.n) { const uint4 sc = __ldg(reinterpret_cast<const uint4*>(A.desc) + 3 * k + 1); if ((sc.y >> 16) != 0 && !(sc.z & DF_LEAN)) which = (sc.z & DF_CHUNKG) ? 1 : 0; }
+    if (in) { const uint4 sc = __ldg(reinterpret_cast<const uint4*>(A.desc) + 3 * k + 1); if ((sc.y >> 16) != 0 && !(sc.z & DF_LEAN)) which = (sc.z & DF_CHUNKG) ? 1 : 0; }
     uint32_t wbase = 0, before = 0;
 #pragma unroll
     for (int l = 0; l < 2; l++) {
@@ -746,6 +751,8 @@ __global__ void derive_q_kernel(TableGeom geom, long long* tables) {
     if (threadIdx.x == 0) { long long a = 0, b = 0; for (int i = 0; i < (int)(blockDim.x >> 5); i++) { a += so[i]; b += sm[i]; } tables[2 * base] = a; tables[2 * base + 1] = b; }
 }
 
+#include "bqsr_count.inl"
+
 }  // namespace
 
 // nibble-packed reference codes of one contig (read by the chunk kernel); 32 bytes of padding on both sides because the
@@ -760,20 +767,157 @@ int pack_reference(elp_ctx* c, int contig) {
         ref_pack_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(c->d_ref[contig], n, c->d_refnib_raw[contig] + 32, n_out);
         LAUNCH_CHECK(c);
     }
+    // one-hot nibbles for the count kernel (bqsr_count.inl); REFHOT_PAD bytes in front (windows of reads at the start of a contig and
+    // the shifted window of an insertion start before base 0), 64 behind
+    if (c->d_refhot_raw[contig]) { cudaFree(c->d_refhot_raw[contig]); c->d_refhot_raw[contig] = nullptr; }
+    CUDA_TRY(c, cudaMalloc(&c->d_refhot_raw[contig], n_out + REFHOT_PAD + 64));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_refhot_raw[contig], 0, n_out + REFHOT_PAD + 64, c->stream));
+    if (n_out) {
+        c->launches++;
+        ref_pack_hot_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, c->stream>>>(c->d_ref[contig], n, c->d_refhot_raw[contig] + REFHOT_PAD, n_out);
+        LAUNCH_CHECK(c);
+    }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return E_OK;
 }
+
+namespace {
+
+// the general kernels (prep -> descriptors -> chunk / warp-per-read kernels with shared-memory counters) over all reads (in_list == nullptr)
+// or over the list bqsr_prep2_kernel left for them
+int gather_general(elp_ctx* c, GatherArgs A, const uint32_t* in_list, uint32_t n_in, double bytes) {
+    const uint64_t n = c->n;
+    const uint64_t n_work = in_list ? (uint64_t)n_in : n;
+    if (!n_work) return E_OK;
+    const int Lc = std::max(1, std::min(c->max_cycle, c->h_ranges.lseq_max));
+    A.Lc = Lc; A.ctx_col_s = 2 * Lc + ((2 * Lc) >> 4) + 1; A.ncols_s = A.ctx_col_s + 16;
+    A.lanes_per_read = std::min(32, std::max(1, (c->h_ranges.lseq_max + CHUNK - 1) / CHUNK));
+    A.in_list = in_list; A.n_in = n_in;
+    for (int q = 0; q < 94; q++) { A.qslot[q] = -1; A.slot_q[q] = 0; }
+    {
+        // slot map: the most frequent QUAL values >= 6 of a sample get shared-memory counters (<= 48 KB per CTA)
+        CUDA_TRY(c, c->scan_tmp.reserve(256 + 4, c->stream));
+        CUDA_TRY(c, cudaMemsetAsync(c->scan_tmp.p, 0, 256 * 4, c->stream));
+        const uint64_t ns = std::min<uint64_t>(c->n_qual, 8u << 20);
+        c->begin("bqsr_g_qual_sample", (double)ns);
+        qual_sample_kernel<<<64, 256, 0, c->stream>>>(c->qual.p, ns, c->scan_tmp.p);
+        c->end(); LAUNCH_CHECK(c);
+        uint32_t h[256];
+        CUDA_TRY(c, cudaMemcpyAsync(h, c->scan_tmp.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        std::vector<int> qs;
+        for (int q = 6; q < 94; q++) if (h[q]) qs.push_back(q);
+        std::sort(qs.begin(), qs.end(), [&](int a, int b) { return h[a] != h[b] ? h[a] > h[b] : a < b; });
+        const size_t per_slot = (size_t)std::max(1, c->geom.n_cov) * A.ncols_s * 4;
+        const int max_slots = (int)std::min<size_t>(63, (48 * 1024) / (2 * per_slot)) - 1;   // observation + mismatch tables, one trash row each
+        A.n_slots = std::max(0, std::min<int>((int)qs.size(), max_slots));
+        for (int s = 0; s < A.n_slots; s++) { A.qslot[qs[s]] = (int8_t)s; A.slot_q[s] = (uint8_t)qs[s]; }
+    }
+    const size_t smem = (size_t)c->geom.n_cov * (A.n_slots + 1) * A.ncols_s * 4 * 2;
+    int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+    // descriptors (48 B/read, indexed by read) and the overflow skip bitmasks live in scratch buffers that are free in this phase
+    CUDA_TRY(c, c->keys_a.reserve(n * 6 + 8, c->stream));
+    CUDA_TRY(c, c->vals_b.reserve(2 * n + 16, c->stream));
+    A.gen_list = c->vals_b.p; A.cg_list = c->vals_b.p + n + 8;
+    A.desc = reinterpret_cast<ReadDesc*>(c->keys_a.p);
+    A.ovf_cap = (uint32_t)std::min<uint64_t>(n, (n >> 4) + 4096);
+    CUDA_TRY(c, c->vals_a.reserve((size_t)A.ovf_cap * OVF_WORDS + 8, c->stream));
+    A.ovf_bits = c->vals_a.p;
+    A.ovf_count = c->scan_tmp.p;   // three u32 (overflow slots, fallback reads, GEN chunk reads), zeroed below
+    A.gen_count = c->scan_tmp.p + 1;
+    CUDA_TRY(c, cudaMemsetAsync(A.ovf_count, 0, 12, c->stream));
+    c->begin("bqsr_g_prep", (double)n_work * (4 * 7 + 2 + 1 + 8 + 8 + 4 + 48) + (double)c->n_cigar * 4 * ((double)n_work / (double)n));
+    bqsr_prep_kernel<<<(unsigned)((n_work + 127) / 128), 128, 0, c->stream>>>(A);
+    c->end(); LAUNCH_CHECK(c);
+    c->begin("bqsr_g_gen_list", (double)n_work * 20);
+    gen_list_kernel<<<(unsigned)((n_work + 255) / 256), 256, 0, c->stream>>>(A);
+    c->end(); LAUNCH_CHECK(c);
+    const uint64_t rpw = 32 / A.lanes_per_read;
+    CUDA_TRY(c, cudaFuncSetAttribute(bqsr_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    CUDA_TRY(c, cudaFuncSetAttribute(bqsr_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    if (!in_list) {
+        const uint64_t steps = (n + rpw - 1) / rpw;
+        uint64_t grid = std::min<uint64_t>((steps + 7) / 8, (uint64_t)sms * CHUNK_MINB);
+        grid = std::max<uint64_t>(grid, (n + (4u << 20) - 1) / (4u << 20));   // <= 4 M reads per CTA keeps the 32-bit shared counters far from overflow
+        c->begin("bqsr_g_chunk", bytes);
+        bqsr_chunk_kernel<false><<<(unsigned)grid, 256, smem, c->stream>>>(A, nullptr, 0);
+        c->end(); LAUNCH_CHECK(c);
+    }
+    uint32_t cnt2[2] = {0, 0};
+    CUDA_TRY(c, cudaMemcpyAsync(cnt2, A.gen_count, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const uint32_t n_gen = cnt2[0], n_cg = cnt2[1];
+    if (n_cg) {
+        const uint64_t steps_g = ((uint64_t)n_cg + rpw - 1) / rpw;
+        const uint64_t grid_cg = std::min<uint64_t>((steps_g + 7) / 8, (uint64_t)sms * CHUNK_MINB);
+        c->begin("bqsr_g_chunk_list", (double)n_cg * (48 + 19 + 8 + 225 + 75));
+        bqsr_chunk_kernel<true><<<(unsigned)grid_cg, 256, smem, c->stream>>>(A, A.cg_list, n_cg);
+        c->end(); LAUNCH_CHECK(c);
+    }
+    if (n_gen) {
+        const size_t smem_g = (size_t)c->geom.n_cov * A.n_slots * (2 * Lc + 1 + 16) * 4 * 2;
+        const uint64_t grid_g = std::min<uint64_t>(((uint64_t)n_gen + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (uint64_t)sms * 4);
+        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_g, 1024)));
+        c->begin("bqsr_g_warp_per_read", (double)n_gen * (48 + 19 + 225 + 150));
+        bqsr_general_kernel<<<(unsigned)grid_g, WARPS_PER_BLOCK * 32, smem_g, c->stream>>>(A, n_gen);
+        c->end(); LAUNCH_CHECK(c);
+    }
+    return E_OK;
+}
+
+// the count kernel's QUAL classifier: an index (q >> sh) & 7 that separates EVERY QUAL value present in the arena, at most four of them >= 6
+struct FastPlan { bool ok = false; int S = 0; uint32_t sh = 0, lut_lo = 0, lut_hi = 0; uint8_t slot_q[4] = {0, 0, 0, 0}; };
+FastPlan plan_fast(const elp_ctx* c, const uint32_t present[4]) {
+    FastPlan P;
+    if (const char* e = getenv("ELPREP_B200_GATHER")) if (std::string(e) == "general") return P;
+    if (present[3] || (present[2] >> 30)) return P;                       // a value > 93 (or a byte >= 128): the general kernels report it
+    std::vector<int> vals;
+    for (int q = 0; q < 94; q++) if ((present[q >> 5] >> (q & 31)) & 1u) vals.push_back(q);
+    std::vector<int> slots;
+    for (int q : vals) if (q >= 6) slots.push_back(q);
+    if (slots.empty() || slots.size() > 4 || vals.size() > 8) return P;
+    if (c->geom.n_cov < 1 || c->geom.n_cov * 2 > MAX_CLS || c->h_ranges.lseq_max > 1024 || c->h_ranges.lseq_max < 1) return P;
+    for (uint32_t sh = 0; sh <= 4; sh++) {
+        uint32_t seen = 0; bool good = true;
+        for (int q : vals) { const uint32_t ix = ((uint32_t)q >> sh) & 7u; if (seen & (1u << ix)) { good = false; break; } seen |= 1u << ix; }
+        if (!good) continue;
+        uint8_t lut[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int q : vals) {
+            uint8_t b = q > 2 ? 0x80 : 0;
+            for (size_t s = 0; s < slots.size(); s++) if (slots[s] == q) b |= (uint8_t)(1u << s);
+            lut[((uint32_t)q >> sh) & 7u] = b;
+        }
+        P.ok = true; P.S = (int)slots.size(); P.sh = sh;
+        P.lut_lo = (uint32_t)lut[0] | ((uint32_t)lut[1] << 8) | ((uint32_t)lut[2] << 16) | ((uint32_t)lut[3] << 24);
+        P.lut_hi = (uint32_t)lut[4] | ((uint32_t)lut[5] << 8) | ((uint32_t)lut[6] << 16) | ((uint32_t)lut[7] << 24);
+        for (size_t s = 0; s < slots.size(); s++) P.slot_q[s] = (uint8_t)slots[s];
+        return P;
+    }
+    return P;
+}
+
+template <int S> int launch_count(elp_ctx* c, const CountArgs& K, bool indel, unsigned grid) {
+    constexpr size_t smem0 = (size_t)CNT_WARPS * (CNT_STAGES * 7 * 512 + CNT_RECRING * 256), smem1 = (size_t)CNT_WARPS * (CNT_STAGES * 9 * 512 + CNT_RECRING * 256);
+    if (!indel) {
+        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_count_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
+        bqsr_count_kernel<S, false><<<grid, CNT_WARPS * 32, smem0, c->stream>>>(K);
+    } else {
+        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_count_kernel<S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+        bqsr_count_kernel<S, true><<<grid, CNT_WARPS * 32, smem1, c->stream>>>(K);
+    }
+    return E_OK;
+}
+
+}  // namespace
 
 int phase_bqsr_gather(elp_ctx* c) {
     if (!c->sorted) return c->fail(E_STATE, "elp_bqsr_gather called before elp_sort_markdup");
     int rc = upload_side_inputs(c);
     if (rc) return rc;
-    for (int i = 0; i < c->n_contigs; i++) if (!c->d_ref[i]) {
-        // a contig without reference bases is only an error if a read maps to it; keep it simple and require all of them
-    }
     const size_t cells = c->geom.cells();
     CUDA_TRY(c, cudaMemsetAsync(c->d_tables, 0, cells * 2 * sizeof(int64_t), c->stream));
     const uint64_t n = c->n;
+    c->gather_eligible = 0;
     if (n) {
         GatherArgs A{};
         A.n = n; A.refid = c->s_refid.p; A.pos = c->s_pos.p; A.nref = c->s_nref.p; A.pnext = c->s_pnext.p; A.tlen = c->s_tlen.p; A.rg = c->s_rg.p; A.lseq = c->s_lseq.p;
@@ -781,81 +925,74 @@ int phase_bqsr_gather(elp_ctx* c) {
         A.cigar = c->cigar.p; A.seq = c->seq.p; A.qual = c->qual.p; A.rg_cov = c->d_rg_cov; A.n_rg = c->n_rg; A.contig_len = c->d_contig_len; A.n_contigs = c->n_contigs;
         A.ref = c->d_ref_ptrs; A.ref_len = c->d_ref_len; A.sites = c->d_site_ptrs; A.n_sites = c->d_n_sites;
         A.geom = c->geom; A.tables = reinterpret_cast<unsigned long long*>(c->d_tables); A.err = c->d_err;
-        // the gather needs up-to-date duplicate flags in output order: s_flag was gathered after duplicate marking
-        uint64_t ref_bytes = 0; for (auto l : c->ref_len) ref_bytes += l;
-        const double bytes = (double)n * (19 + 4 + 8 + 8) + (double)c->n_cigar * 4 + (double)c->n_seq + (double)c->n_qual + (double)ref_bytes;
-        // slot map: the most frequent QUAL values >= 6 of a sample get shared-memory counters (<= 48 KB per CTA)
-        const int Lc = std::max(1, std::min(c->max_cycle, c->h_ranges.lseq_max));
-        A.Lc = Lc; A.ctx_col_s = 2 * Lc + ((2 * Lc) >> 4) + 1; A.ncols_s = A.ctx_col_s + 16;
-        A.lanes_per_read = std::min(32, std::max(1, (c->h_ranges.lseq_max + CHUNK - 1) / CHUNK));
         A.refnib = c->d_refnib_ptrs;
-        for (int q = 0; q < 94; q++) { A.qslot[q] = -1; A.slot_q[q] = 0; }
-        {
-            CUDA_TRY(c, c->scan_tmp.reserve(256 + 4, c->stream));
-            CUDA_TRY(c, cudaMemsetAsync(c->scan_tmp.p, 0, 256 * 4, c->stream));
-            const uint64_t ns = std::min<uint64_t>(c->n_qual, 8u << 20);
-            c->begin("qual_sample", (double)ns);
-            qual_sample_kernel<<<64, 256, 0, c->stream>>>(c->qual.p, ns, c->scan_tmp.p);
-            c->end(); LAUNCH_CHECK(c);
-            uint32_t h[256];
-            CUDA_TRY(c, cudaMemcpyAsync(h, c->scan_tmp.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-            std::vector<int> qs;
-            for (int q = 6; q < 94; q++) if (h[q]) qs.push_back(q);
-            std::sort(qs.begin(), qs.end(), [&](int a, int b) { return h[a] != h[b] ? h[a] > h[b] : a < b; });
-            const size_t per_slot = (size_t)std::max(1, c->geom.n_cov) * A.ncols_s * 4;
-            const int max_slots = (int)std::min<size_t>(63, (48 * 1024) / (2 * per_slot)) - 1;   // observation + mismatch tables, one trash row each
-            A.n_slots = std::max(0, std::min<int>((int)qs.size(), max_slots));
-            for (int s = 0; s < A.n_slots; s++) { A.qslot[qs[s]] = (int8_t)s; A.slot_q[s] = (uint8_t)qs[s]; }
-        }
-        const size_t smem = (size_t)c->geom.n_cov * (A.n_slots + 1) * A.ncols_s * 4 * 2;
-        int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-        // descriptors (32 B/read) and the overflow skip bitmasks live in scratch buffers that are free in this phase
-        CUDA_TRY(c, c->keys_a.reserve(n * 6 + 8, c->stream));
-        CUDA_TRY(c, c->vals_b.reserve(2 * n + 16, c->stream));
-        A.gen_list = c->vals_b.p; A.cg_list = c->vals_b.p + n + 8;
-        A.desc = reinterpret_cast<ReadDesc*>(c->keys_a.p);
-        A.ovf_cap = (uint32_t)std::min<uint64_t>(n, (n >> 4) + 4096);
-        CUDA_TRY(c, c->vals_a.reserve((size_t)A.ovf_cap * OVF_WORDS + 8, c->stream));
-        A.ovf_bits = c->vals_a.p;
-        A.ovf_count = c->scan_tmp.p;   // three u32 (overflow slots, fallback reads, GEN chunk reads), zeroed below
-        A.gen_count = c->scan_tmp.p + 1;
-        CUDA_TRY(c, cudaMemsetAsync(A.ovf_count, 0, 12, c->stream));
-        c->begin("bqsr_prep", (double)n * (4 * 7 + 2 + 1 + 8 + 8 + 4 + 48) + (double)c->n_cigar * 4);
-        bqsr_prep_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->stream>>>(A);
-        c->end(); LAUNCH_CHECK(c);
-        c->begin("bqsr_gen_list", (double)n * 20);
-        gen_list_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(A);
-        c->end(); LAUNCH_CHECK(c);
-        const uint64_t rpw = 32 / A.lanes_per_read, steps = (n + rpw - 1) / rpw;
-        uint64_t grid = std::min<uint64_t>((steps + 7) / 8, (uint64_t)sms * CHUNK_MINB);
-        grid = std::max<uint64_t>(grid, (n + (4u << 20) - 1) / (4u << 20));   // <= 4 M reads per CTA keeps the 32-bit shared counters far from overflow
-        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_chunk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-        CUDA_TRY(c, cudaFuncSetAttribute(bqsr_chunk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
-        c->begin("bqsr_gather", bytes);
-        bqsr_chunk_kernel<false><<<(unsigned)grid, 256, smem, c->stream>>>(A, nullptr, 0);
-        c->end(); LAUNCH_CHECK(c);
-        uint32_t cnt2[2] = {0, 0};
-        CUDA_TRY(c, cudaMemcpyAsync(cnt2, A.gen_count, 8, cudaMemcpyDeviceToHost, c->stream));
+        uint64_t ref_bytes = 0; for (auto l : c->ref_len) ref_bytes += l;
+        // N_eligible * (19 + 4 + 4 c + L/2 + L) + genome bytes once; per-read averages of the arenas stand in for c and L
+        const double per_read = 23.0 + ((double)c->n_cigar * 4 + (double)(c->n_seq - ARENA_FRONT_PAD) + (double)(c->n_qual - ARENA_FRONT_PAD)) / (double)n;
+        uint32_t present[4] = {0, 0, 0, 0};
+        CUDA_TRY(c, cudaMemcpyAsync(present, c->d_qpresent, 16, cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        const uint32_t n_gen = cnt2[0], n_cg = cnt2[1];
-        if (n_cg) {
-            const uint64_t steps_g = ((uint64_t)n_cg + rpw - 1) / rpw;
-            const uint64_t grid_cg = std::min<uint64_t>((steps_g + 7) / 8, (uint64_t)sms * CHUNK_MINB);
-            c->begin("bqsr_gather_indel", (double)n_cg * (48 + 19 + 8 + 225 + 75));
-            bqsr_chunk_kernel<true><<<(unsigned)grid_cg, 256, smem, c->stream>>>(A, A.cg_list, n_cg);
+        const FastPlan F = plan_fast(c, present);
+        if (!F.ok) {
+            // eligible reads are not counted on this path: the roofline line charges all reads (an upper bound, stated in DESIGN.md)
+            c->gather_eligible = n;
+            rc = gather_general(c, A, nullptr, 0, (double)n * per_read + (double)ref_bytes);
+            if (rc) return rc;
+        } else {
+            const int n_cls = 2 * c->geom.n_cov;
+            const int lpr = std::min(32, std::max(1, (c->h_ranges.lseq_max + 31) / 32)), rpw = 32 / lpr;
+            int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+            // small device words: [0,64) class histogram | [64,129) region bases | [136,265) list counters | [272,274) segment counts | [276,278) queue heads
+            uint32_t* sm = c->d_bq_small;
+            uint32_t *d_hist = sm, *d_region = sm + 64, *d_keycnt = sm + 136, *d_nseg = sm + 272, *d_next = sm + 276;
+            CUDA_TRY(c, cudaMemsetAsync(sm, 0, 512 * 4, c->stream));
+            const uint64_t seg_cap = n / ((uint64_t)SEG_PASSES * rpw) + 2 * MAX_CLS + 16;
+            CUDA_TRY(c, c->bq_recs.reserve(2 * n + 8, c->stream));
+            CUDA_TRY(c, c->bq_segs.reserve(2 * seg_cap, c->stream));
+            CUDA_TRY(c, c->mate.reserve(n + 4, c->stream));
+            c->begin("bqsr_g_class_hist", (double)n * 6);
+            class_hist_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)sms * 8), 256, 0, c->stream>>>(n, A.rg, A.flag, A.rg_cov, A.n_rg, n_cls, d_hist);
+            class_scan_kernel<<<1, 32, 0, c->stream>>>(n_cls, d_hist, d_region);
+            c->end(); LAUNCH_CHECK(c); c->launches++;
+            Prep2Args P{};
+            P.n_cls = n_cls; P.region_base = d_region; P.key_count = d_keycnt; P.recs = c->bq_recs.p; P.cx_list = c->mate.p; P.lpr = lpr; P.max_cycle = c->max_cycle;
+            c->begin("bqsr_g_prep2", (double)n * (4 * 7 + 2 + 1 + 8 + 8 + 4 + 8) + (double)c->n_cigar * 4);
+            bqsr_prep2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(A, P);
             c->end(); LAUNCH_CHECK(c);
-        }
-        if (n_gen) {
-            const size_t smem_g = (size_t)c->geom.n_cov * A.n_slots * (2 * Lc + 1 + 16) * 4 * 2;
-            const uint64_t grid_g = std::min<uint64_t>(((uint64_t)n_gen + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK, (uint64_t)sms * 4);
-            CUDA_TRY(c, cudaFuncSetAttribute(bqsr_general_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem_g, 1024)));
-            c->begin("bqsr_gather_general", (double)n_gen * (48 + 19 + 225 + 150));
-            bqsr_general_kernel<<<(unsigned)grid_g, WARPS_PER_BLOCK * 32, smem_g, c->stream>>>(A, n_gen);
-            c->end(); LAUNCH_CHECK(c);
+            uint4* segs0 = c->bq_segs.p; uint4* segs1 = c->bq_segs.p + seg_cap;
+            seg_build_kernel<<<1, 128, 0, c->stream>>>(n_cls, rpw, d_region, d_keycnt, segs0, segs1, d_nseg);
+            c->launches++; LAUNCH_CHECK(c);
+            CountArgs K{};
+            K.qual = c->qual.p; K.seq = c->seq.p; K.refhot = c->d_refhot_ptrs; K.recs = c->bq_recs.p; K.tables = A.tables; K.geom = c->geom;
+            K.lpr = lpr; K.rpw = rpw; K.sh = F.sh; K.lut_lo = F.lut_lo; K.lut_hi = F.lut_hi;
+            for (int s = 0; s < 4; s++) K.slot_q[s] = F.slot_q[s];
+            const unsigned grid = (unsigned)sms * 2;
+            for (int v = 0; v < 2; v++) {
+                K.segs = v ? segs1 : segs0; K.n_seg = d_nseg + v; K.seg_next = d_next + v;
+                c->begin(v ? "bqsr_g_count_indel" : "bqsr_g_count", 0);     // bytes are set below, once the list sizes are known
+                switch (F.S) {
+                    case 1: rc = launch_count<1>(c, K, v != 0, grid); break;
+                    case 2: rc = launch_count<2>(c, K, v != 0, grid); break;
+                    case 3: rc = launch_count<3>(c, K, v != 0, grid); break;
+                    default: rc = launch_count<4>(c, K, v != 0, grid); break;
+                }
+                c->end();
+                if (rc) return rc;
+                LAUNCH_CHECK(c);
+            }
+            std::vector<uint32_t> kc(2 * n_cls + 1);
+            CUDA_TRY(c, cudaMemcpyAsync(kc.data(), d_keycnt, kc.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+            uint64_t n_simple = 0, n_indel = 0;
+            for (int k = 0; k < 2 * n_cls; k++) (k & 1 ? n_indel : n_simple) += kc[k];
+            const uint32_t n_cx = kc[2 * n_cls];
+            c->gather_eligible = n_simple + n_indel + n_cx;
+            c->set_pending_bytes("bqsr_g_count", (double)n_simple * (per_read + 32) + (double)ref_bytes);
+            c->set_pending_bytes("bqsr_g_count_indel", (double)n_indel * (per_read + 32));
+            if (n_cx) { rc = gather_general(c, A, c->mate.p, n_cx, 0); if (rc) return rc; }
         }
     }
-    c->begin("bqsr_derive_q", 0);
+    c->begin("bqsr_g_derive_q", 0);
     derive_q_kernel<<<c->geom.n_cov * 94, 256, 0, c->stream>>>(c->geom, reinterpret_cast<long long*>(c->d_tables));
     c->end(); LAUNCH_CHECK(c);
     rc = check_device_errors(c);

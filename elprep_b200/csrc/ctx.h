@@ -33,6 +33,8 @@ template <class T> struct DBuf {
 // duplication metrics of one library (filters.DuplicatesCtr, mark-optical-duplicates.go:95-110): the seven counters in the
 // reference's field order and the three count histograms (all, non-optical, optical)
 struct DupCounters { int64_t ctr[7] = {0, 0, 0, 0, 0, 0, 0}; std::map<int64_t, int64_t> hist[3]; };
+#define REFHOT_PAD 512
+#define ARENA_FRONT_PAD 64   // QUAL / SEQ arenas start at this offset: kernels read aligned windows that may begin before a read
 #define OPT_NCTR 8
 #define OPT_HBINS 1024
 #define OPT_OVF_CAP (1 << 16)
@@ -79,6 +81,8 @@ struct elp_ctx {
     const uint8_t** d_ref_ptrs = nullptr; // [n_contigs] device array of pointers
     std::vector<uint8_t*> d_refnib_raw;   // per contig: 4-bit reference codes (bqsr_gather.cu pack_reference), payload at +32
     const uint8_t** d_refnib_ptrs = nullptr;
+    std::vector<uint8_t*> d_refhot_raw;   // per contig: one-hot reference nibbles for the count kernel (bqsr_count.inl), payload at +REFHOT_PAD
+    const uint8_t** d_refhot_ptrs = nullptr;
     uint64_t* d_ref_len = nullptr;
     std::vector<int32_t*> d_sites;        // per contig, (start,end) pairs
     std::vector<uint64_t> n_sites;
@@ -117,6 +121,9 @@ struct elp_ctx {
     DBuf<uint32_t> mate;                      // [n] mate index or 0xffffffff
     DBuf<uint32_t> pair_a, pair_b, scan_tmp, scan_blk;
     DBuf<uint8_t> bytes_tmp;
+    DBuf<uint4> bq_recs, bq_segs;             // BQSR count kernel: work records of the eligible reads, segment table
+    uint32_t* d_bq_small = nullptr;           // class histogram, region bases, list counters, segment counts, work-queue heads
+    uint32_t* d_qpresent = nullptr;           // [4] bit q set iff QUAL value q (0..127) occurs in the arena (maintained at ingest)
 
     // ---- output order ----
     bool sorted = false;                      // columns below valid
@@ -135,6 +142,7 @@ struct elp_ctx {
     std::vector<int64_t> h_tables;
     std::vector<uint8_t> h_emp;               // [cells]
     bool gathered = false, finalized = false;
+    uint64_t gather_eligible = 0;             // reads the last elp_bqsr_gather recalibrated (what the roofline line charges)
     uint8_t* d_lut = nullptr;                 // [n_cov][94][2*lut_maxcyc+1][17]
     int lut_maxcyc = 0;
     size_t lut_cap = 0;
@@ -174,6 +182,7 @@ struct elp_ctx {
         if (!profile) return;
         cudaEventRecord(pending.back().b, stream);
     }
+    void set_pending_bytes(const char* name, double bytes) { for (auto& pe : pending) if (pe.name == name) pe.alg_bytes = bytes; }
     void resolve_events() {
         if (pending.empty()) return;
         cudaStreamSynchronize(stream);
@@ -210,3 +219,4 @@ int build_apply_lut(elp_ctx* c, int Lc);   // bqsr_finalize.cu
 int upload_side_inputs(elp_ctx* c);
 int pack_reference(elp_ctx* c, int contig);
 int check_device_errors(elp_ctx* c);
+int qual_presence_update(elp_ctx* c, uint64_t first_byte, uint64_t n_bytes);   // api.cu: called by both ingest paths

@@ -1,0 +1,14 @@
+"""CPU check of the word-parallel lane arithmetic of the BQSR count kernel: tests/c/lane_check.cpp compiles the kernel's own header
+(elprep_b200/csrc/bqsr_lane.cuh) as host C++ and compares it base by base with a direct restatement of the per-base rules of
+(*BaseRecalibrator).Recalibrate (filters/bqsr.go:467-551) on random reads, windows cut out of byte arenas as on the device."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_lane_arithmetic_matches_per_base_rules(tmp_path):
+    exe = str(tmp_path / "lane_check")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "elprep_b200", "csrc"), "-o", exe, os.path.join(ROOT, "tests", "c", "lane_check.cpp")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout[-2000:]
