@@ -68,60 +68,19 @@ __global__ void __launch_bounds__(256) bqsr_prep2_kernel(GatherArgs A, Prep2Args
         if (elig && pos0 > A.contig_len[refid]) elig = false;
         if (elig) {
             key = 2 * P.n_cls;   // general path unless the shape below matches
-            // ---- CIGAR shape ----
             const uint64_t coff = A.cigar_off[k];
-            int i = 0, a = 0, b = 0, m1 = 0, m2 = 0, d = 0, dop = -1;
-            bool shape = nc0 >= 1 && nc0 <= 9;
-            uint32_t op = 0;
-            auto next = [&]() { op = (i < nc0) ? __ldg(A.cigar + coff + i) : 0xfu; i++; };   // 0xf: end marker (op code 15 does not exist)
+            const lanes::ClipShape cs = lanes::closed_form_clip((uint32_t)f, pos0, A.pnext[k], A.tlen[k], A.nref[k], L0, nc0, [&](int i) { return __ldg(A.cigar + coff + i); });
+            bool shape = cs.kind == 0 || cs.kind == 1;
+            if (cs.kind < 0) key = KEY_NONE;
+            const int dop = cs.kind == 1 ? (cs.ins ? 1 : 2) : -1, ins = cs.ins, del = cs.del, lo = cs.lo, m1 = cs.bp;
+            const int32_t cpos = cs.cpos;
+            const int Lk = cs.hi - cs.lo;
             if (shape) {
-                next();
-                while (op_of(op) == 5 && i <= nc0) next();
-                if (op_of(op) == 4) { a = len_of(op); next(); }
-                const int o1 = op_of(op);
-                if ((o1 == 0 || o1 == 7 || o1 == 8) && len_of(op) > 0) { m1 = len_of(op); next(); } else shape = false;
-                if (shape && (op_of(op) == 1 || op_of(op) == 2) && len_of(op) > 0) {
-                    dop = op_of(op); d = len_of(op); next();
-                    const int o2 = op_of(op);
-                    if ((o2 == 0 || o2 == 7 || o2 == 8) && len_of(op) > 0) { m2 = len_of(op); next(); } else shape = false;
-                }
-                if (shape && op_of(op) == 4 && i <= nc0) { b = len_of(op); next(); }
-                while (shape && op_of(op) == 5 && i <= nc0) next();
-                if (shape && i != nc0 + 1) shape = false;              // something else follows
-                if (shape && (a < 0 || b < 0)) shape = false;
+                const int kept_ref = Lk - ins + del;
+                if (Lk > P.max_cycle || Lk > 32 * P.lpr || Lk > 2047 || ins > 255 || del > 4095 || refid >= (1 << 23) ||
+                    (uint64_t)(cpos - 1) + (uint64_t)kept_ref > A.ref_len[refid]) shape = false;
             }
-            const int ins = dop == 1 ? d : 0, del = dop == 2 ? d : 0;
-            if (shape && a + m1 + ins + m2 + b != L0) { shape = false; key = KEY_NONE; }    // SEQ length != read length of the CIGAR: not recalibrated (bqsr.go:236-238)
-            if (shape) {
-                int lo = a, hi = a + m1 + ins + m2;              // kept bases [lo, hi) of the stored read
-                int32_t cpos = pos0;
-                const int reflen = m1 + m2 + del;
-                // ---- hardClipAdaptorSequence (utils.go:148-222) ----
-                const int32_t pnext = A.pnext[k], tlen = A.tlen[k], nref = A.nref[k];
-                const bool next_unmapped = (f & F_NEXTUNMAPPED) || nref < 0 || pnext == 0;
-                bool well = false; const int alnEnd = pos0 + reflen - 1;
-                if (tlen != 0 && (f & F_MULTIPLE) && !next_unmapped && (((f & F_REVERSED) != 0) != ((f & F_NEXTREVERSED) != 0))) {
-                    if (f & F_REVERSED) well = alnEnd > pnext; else well = pos0 <= pnext + tlen;
-                }
-                bool adaptor = false; int boundary = 0;
-                if (well) {
-                    boundary = (f & F_REVERSED) ? (int)pnext - 1 : (int)pos0 + (tlen < 0 ? -tlen : tlen);
-                    adaptor = boundary >= pos0 && boundary <= alnEnd;
-                }
-                if (adaptor) {
-                    if (dop >= 0) shape = false;                 // reference -> read coordinates through an indel: general path
-                    else {
-                        const int rc = boundary - (pos0 - a);    // read coordinate of the boundary (linear for S/M-only CIGARs)
-                        if (f & F_REVERSED) { lo = rc + 1; cpos = boundary + 1; } else hi = rc;
-                    }
-                }
-                const int Lk = hi - lo;
-                if (shape && Lk <= 0) { shape = false; key = KEY_NONE; }        // clipped away: dropped (bqsr.go:483-490)
-                if (shape) {
-                    const int kept_ref = Lk - ins + del;
-                    if (Lk > P.max_cycle || Lk > 32 * P.lpr || Lk > 2047 || ins > 255 || del > 4095 || refid >= (1 << 23) ||
-                        (uint64_t)(cpos - 1) + (uint64_t)kept_ref > A.ref_len[refid]) shape = false;
-                }
+            {
                 // ---- known sites (calculateSkipSlice, bqsr.go:389-414): read coordinates are linear without an indel ----
                 if (shape) {
                     const uint64_t ns = A.n_sites[refid];

@@ -139,6 +139,56 @@ LANE_FN uint32_t onehot4(uint32_t a, uint32_t c, uint32_t g, uint32_t t) {
     return (acg ^ t) & ~((a & c) | (ac & g) | (acg & t));
 }
 
+// ---- closed-form read clipping (what bqsr_prep2_kernel does per read; host-checkable against the oracle's step-by-step clipping) ----
+// hardClipAdaptorSequence + hardClipSoftClippedBases (filters/utils.go:148-222, 506-534) have a closed form for two CIGAR shapes:
+//   [H..][S a] M m [S b][H..]                    the adaptor boundary maps to read coordinate boundary - (POS - a): no D/N/I to fall into,
+//                                                so computeReadCoordinateForReferenceCoordinate (:267-326) is linear and never fails
+//   [H..][S a] M m1 (I|D) d M m2 [S b][H..]     only when no adaptor clipping applies (the mapping through an indel has quirks)
+// kind: -1 the read is not recalibrated (SEQ length != CIGAR read length, or clipped away), 0 / 1 the two shapes, 2 anything else
+// (general path).  Kept bases [lo, hi) of the stored read, cpos = POS of the first kept base; bp = kept-read index of the indel.
+struct ClipShape { int kind, lo, hi, cpos, bp, ins, del; };
+template <class CigarAt>
+LANE_FN ClipShape closed_form_clip(uint32_t f, int pos0, int pnext, int tlen, int nref, int L0, int nc0, CigarAt cigar_at) {
+    ClipShape R; R.kind = 2; R.lo = R.hi = 0; R.cpos = pos0; R.bp = R.ins = R.del = 0;
+    if (nc0 < 1 || nc0 > 9) return R;
+    int i = 0, a = 0, b = 0, m1 = 0, m2 = 0, d = 0, dop = -1;
+    uint32_t op = 0;
+    auto nxt = [&]() { op = (i < nc0) ? cigar_at(i) : 0xfu; i++; };      // 0xf: end marker (operation code 15 does not exist)
+    auto opc = [&]() { return (int)(op & 15u); };
+    auto opl = [&]() { return (int)(op >> 4); };
+    nxt();
+    while (opc() == 5 && i <= nc0) nxt();
+    if (opc() == 4) { a = opl(); nxt(); }
+    if ((opc() == 0 || opc() == 7 || opc() == 8) && opl() > 0) { m1 = opl(); nxt(); } else return R;
+    if ((opc() == 1 || opc() == 2) && opl() > 0) {
+        dop = opc(); d = opl(); nxt();
+        if ((opc() == 0 || opc() == 7 || opc() == 8) && opl() > 0) { m2 = opl(); nxt(); } else return R;
+    }
+    if (opc() == 4 && i <= nc0) { b = opl(); nxt(); }
+    while (opc() == 5 && i <= nc0) nxt();
+    if (i != nc0 + 1) return R;                                             // something else follows
+    const int ins = dop == 1 ? d : 0, del = dop == 2 ? d : 0;
+    if (a + m1 + ins + m2 + b != L0) { R.kind = -1; return R; }             // SEQ length != read length of the CIGAR (bqsr.go:236-238)
+    int lo = a, hi = a + m1 + ins + m2, cpos = pos0;
+    const int alnEnd = pos0 + m1 + m2 + del - 1;
+    // hardClipAdaptorSequence (utils.go:148-222)
+    const bool paired = (f & 0x1u) != 0, rev = (f & 0x10u) != 0, nrev = (f & 0x20u) != 0;
+    const bool next_unmapped = (f & 0x8u) || nref < 0 || pnext == 0;          // isStrictNextUnmapped (utils.go:144)
+    bool well = false;
+    if (tlen != 0 && paired && !next_unmapped && rev != nrev) well = rev ? (alnEnd > pnext) : (pos0 <= pnext + tlen);
+    if (well) {
+        const int boundary = rev ? pnext - 1 : pos0 + (tlen < 0 ? -tlen : tlen);
+        if (boundary >= pos0 && boundary <= alnEnd) {
+            if (dop >= 0) return R;                                         // through an indel: general path
+            const int rc = boundary - (pos0 - a);                          // read coordinate of the boundary
+            if (rev) { lo = rc + 1; cpos = boundary + 1; } else hi = rc;
+        }
+    }
+    if (hi - lo <= 0) { R.kind = -1; return R; }                            // clipped away: dropped (bqsr.go:483-490)
+    R.kind = dop >= 0 ? 1 : 0; R.lo = lo; R.hi = hi; R.cpos = cpos; R.bp = m1; R.ins = ins; R.del = del;
+    return R;
+}
+
 // ---- one pass of one lane, in three stages separated by the two cross-lane steps of the count kernel --------------------------------
 // (RT is a callable n -> range_plane(clamp(n, 0, 32)): a shared-memory table on the device, the function itself on the host)
 struct LaneRec {            // the fields of a 32-byte work record that the lane arithmetic needs
