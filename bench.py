@@ -135,7 +135,7 @@ def verify_against_oracle(ctx, w, out_np, n_reads, threads):
     oracle.bqsr_apply(srt, w.header, tb, n_threads=threads)
     o_tables, o_emp = oracle_tables_dense(tb)
     nq = int(qoff[n_reads])
-    checks = {"order": bool(np.array_equal(idx[:n_reads], perm.astype(np.uint64))), "flag": bool(np.array_equal(flag[:n_reads], srt.flag)),
+    checks = {"order": bool(np.array_equal(idx[:n_reads].astype(np.uint64), perm.astype(np.uint64))), "flag": bool(np.array_equal(flag[:n_reads], srt.flag)),
               "tables": bool(np.array_equal(g_tables, o_tables)), "empirical_quality": bool(np.array_equal(g_emp, o_emp)),
               "qual": bool(nq == srt.qual.size and np.array_equal(qual[:nq], srt.qual))}
     return {"ok": all(checks.values()), "checks": checks, "reads": int(n_reads), "duplicates": int(((flag[:n_reads] & 0x400) != 0).sum()),
@@ -197,47 +197,62 @@ def main():
     hb = pinned(w.batch)
     n_reads = hb.n
     h2d = sum(getattr(hb, f).nbytes for f in hb.FIELDS)
-    ctx = device.Context(w.header, device=local, profile=True)
-    for ci in range(len(contigs)):
-        ctx.set_reference(ci, w.contig_bases[ci])
-        ctx.set_known_sites(ci, w.sites[ci], already_flat=True)
-    ctx.reserve(n_reads, int(hb.qual.size), int(hb.cigar.size), int(hb.qname.size))
-    # pinned output buffers for the fetch
-    out = tuple(torch.empty(s, dtype=dt, pin_memory=True) for s, dt in ((n_reads, torch.int64), (n_reads, torch.int16), (n_reads + 1, torch.int64), (int(hb.qual.size), torch.uint8)))
-    out_np = (out[0].numpy().view(np.uint64), out[1].numpy().view(np.uint16), out[2].numpy().view(np.uint64), out[3].numpy())
+
+    def make_ctx():
+        cx = device.Context(w.header, device=local, profile=True)
+        for ci in range(len(contigs)):
+            cx.set_reference(ci, w.contig_bases[ci])
+            cx.set_known_sites(ci, w.sites[ci], already_flat=True)
+        cx.reserve(n_reads, int(hb.qual.size), int(hb.cigar.size), int(hb.qname.size))
+        return cx
+    ctx = make_ctx()
+    # pinned output buffers for the fetch: 32-bit record indices, FLAG, QUAL offsets, QUAL bytes
+    out = tuple(torch.empty(s, dtype=dt, pin_memory=True) for s, dt in ((n_reads, torch.int32), (n_reads, torch.int16), (n_reads + 1, torch.int64), (int(hb.qual.size), torch.uint8)))
+    out_np = (out[0].numpy().view(np.uint32), out[1].numpy().view(np.uint16), out[2].numpy().view(np.uint64), out[3].numpy())
     d2h = sum(a.nbytes for a in out_np)
-    tables_t = None
-    if world > 1:
-        ptr, nvals = ctx.tables_device()
+
+    def alias_tables(cx):
+        ptr, nvals = cx.tables_device()
 
         class _Alias:
             __cuda_array_interface__ = {"shape": (nvals,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-        tables_t = torch.as_tensor(_Alias(), device=f"cuda:{local}")
+        return torch.as_tensor(_Alias(), device=f"cuda:{local}")
+    tables_t = {id(ctx): alias_tables(ctx)} if world > 1 else {}
 
-    def barrier():
-        ctx.synchronize(); torch.cuda.synchronize()
+    def barrier(cx):
+        cx.synchronize(); torch.cuda.synchronize()
         if dist:
             dist.barrier(); torch.cuda.synchronize()
 
-    def step():
-        ctx.reset()
-        barrier()
-        ctx.timer_start()                       # ---- e2e region: host buffers in, host buffers out
-        ctx.append(hb)
-        e_mid = ctx.timer_stop()
-        ctx.timer_start()                       # ---- device-resident region
-        ctx.sort_markdup(device.SO_COORDINATE, True)
-        ctx.bqsr_gather()
+    def phases(cx):
+        """the device-resident hot path of one step; returns the time this rank spent in the collective (ms, host clock around a synchronised allreduce)"""
+        cx.sort_markdup(device.SO_COORDINATE, True)
+        cx.bqsr_gather()
+        t_coll = 0.0
         if dist:
-            ctx.tables_device()
-            dist.all_reduce(tables_t); torch.cuda.synchronize()
-        ctx.bqsr_finalize(None)
-        ctx.bqsr_apply()
+            cx.tables_device()
+            t0 = time.perf_counter()
+            dist.all_reduce(tables_t[id(cx)]); torch.cuda.synchronize()
+            t_coll = 1e3 * (time.perf_counter() - t0)
+        cx.bqsr_finalize(None)
+        cx.bqsr_apply()
+        return t_coll
+
+    def step():
+        """one step with nothing overlapped: upload | barrier | device-resident region (the `value` clock) | download"""
+        ctx.reset()
+        barrier(ctx)
+        ctx.timer_start()
+        ctx.append(hb)
+        t_in = ctx.timer_stop()
+        barrier(ctx)                            # every rank's reads are resident before any rank starts the device-resident clock
+        ctx.timer_start()
+        t_coll = phases(ctx)
         t_dev = ctx.timer_stop()
         ctx.timer_start()
-        ctx.fetch(0, n_reads, True, out_np)
-        e_out = ctx.timer_stop()
-        return t_dev, e_mid + t_dev + e_out
+        ctx.fetch_async(out_np); ctx.fetch_wait()
+        t_out = ctx.timer_stop()
+        return t_dev, t_in, t_out, t_coll
 
     for _ in range(args.warmup):
         step()
@@ -245,19 +260,51 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    dev_ms, e2e_ms = [], []
+    dev_ms, in_ms, out_ms, coll_ms = [], [], [], []
     for _ in range(args.steps):
-        a, b = step()
-        dev_ms.append(a); e2e_ms.append(b)
-    clocks = sampler.stop() if rank == 0 else None
+        a, b, c_, d_ = step()
+        dev_ms.append(a); in_ms.append(b); out_ms.append(c_); coll_ms.append(d_)
     launches = ctx.launch_count()
     stats = ctx.kernel_stats()
-    tot = torch.tensor([float(np.sum(dev_ms)), float(np.sum(e2e_ms))], device=f"cuda:{local}", dtype=torch.float64)
+    # ---- e2e: the same K steps through the public API with host buffers, software-pipelined over two contexts: while context A's
+    # batch uploads, context B (previous step) runs its device phases and downloads.  Every step still moves its full input and output.
+    ctx2 = make_ctx()
+    if world > 1:
+        tables_t[id(ctx2)] = alias_tables(ctx2)
+    cs = (ctx, ctx2)
+
+    def e2e_run(k_steps):
+        for s in range(k_steps + 1):
+            cur = cs[s % 2] if s < k_steps else None
+            prev = cs[(s - 1) % 2] if s >= 1 else None
+            if cur is not None:
+                cur.reset(); cur.append_async(hb)
+            if prev is not None:
+                phases(prev); prev.fetch_async(out_np)
+            if cur is not None:
+                cur.append_wait()
+            if prev is not None:
+                prev.fetch_wait()
+    e2e_run(2)                                   # warm-up (allocations of the second context)
+    barrier(ctx); ctx2.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    e2e_run(args.steps)
+    ctx.synchronize(); ctx2.synchronize(); torch.cuda.synchronize()
+    ev1.record(); ev1.synchronize()
+    e2e_ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    tot = torch.tensor([float(np.sum(dev_ms)), float(e2e_ms_total)], device=f"cuda:{local}", dtype=torch.float64)
     cnt = torch.tensor([float(n_reads)], device=f"cuda:{local}", dtype=torch.float64)
+    ph = torch.tensor([float(np.mean(in_ms)), float(np.mean(dev_ms)), float(np.mean(coll_ms)), float(np.mean(out_ms))], device=f"cuda:{local}", dtype=torch.float64)
+    ph_all = [ph]
     if dist:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        ph_all = [torch.zeros_like(ph) for _ in range(world)]
+        dist.all_gather(ph_all, ph)
     dev_total_ms, e2e_total_ms = tot.tolist()
     total_reads = cnt.item()
+    phases_per_rank = [{"rank": r, "append_ms": p[0], "device_ms": p[1], "collective_ms": p[2], "fetch_ms": p[3]} for r, p in enumerate(x.tolist() for x in ph_all)]
     if rank != 0:
         if dist:
             dist.barrier(); dist.destroy_process_group()
@@ -271,23 +318,27 @@ def main():
     except Exception:
         pass
     peak, peak_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json hbm_gbs)") if peaks.get("hbm_gbs") else (6650.0, "fallback (B200_PROFILING.md)")
-    dom = max(stats.items(), key=lambda kv: kv[1]["ms"]) if stats else (None, None)
-    roof = None
-    if dom[0]:
-        k = dom[1]
-        ach = k["alg_bytes"] / (k["ms"] / 1e3) / 1e9
-        # DRAM bytes per launch of that kernel from an `ncu --set full` capture of this same workload (profiles/*_traffic.json,
-        # written by hand from the capture named in it); only used when the capture was taken on the same number of reads
+    def roof_of(names, label, traffic_key=None):
+        ks = [stats[nm] for nm in names if nm in stats]
+        if not ks:
+            return None
+        ms, by, ln = sum(k["ms"] for k in ks), sum(k["alg_bytes"] for k in ks), sum(k["launches"] for k in ks)
+        ach = by / (ms / 1e3) / 1e9 if ms > 0 else None
         traffic = None
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-            ent = tr["kernels"].get(dom[0])
+        try:   # DRAM bytes per launch from an `ncu --set full` capture of this same workload and build (profiles/r02_traffic.json names the capture)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            ent = tr["kernels"].get(traffic_key or names[0])
             if ent and abs(tr["reads"] - n_reads) <= 0.01 * n_reads and world == 1:
                 traffic = ent["dram_bytes_per_launch"]
         except Exception:
             pass
-        roof = {"bound": "hbm", "kernel": dom[0], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                "launches": k["launches"], "avg_launch_ms": k["ms"] / max(1, k["launches"]), "alg_bytes_per_launch": k["alg_bytes"] / max(1, k["launches"])}
+        return {"bound": "hbm", "kernel": label, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak if ach else None, "traffic": traffic, "peak_source": peak_src,
+                "launches": ln, "avg_launch_ms": ms / max(1, ln), "alg_bytes_per_launch": by / max(1, ln), "ms_per_step": ms / args.steps}
+    dom = max(stats.items(), key=lambda kv: kv[1]["ms"]) if stats else (None, None)
+    roof = roof_of([dom[0]], dom[0]) if dom[0] else None
+    gather_names = [k for k in stats if k.startswith("bqsr_g_")]
+    graded = {"radix_sort": roof_of(["radix_onesweep_u64"], "radix_onesweep_u64 (one digit pass: N*2*(8+4) B)"),
+              "covariate_histogram": roof_of(gather_names, "elp_bqsr_gather: " + "+".join(sorted(gather_names)) + " (N_eligible*(19+4+4c+L/2+L) + genome once)", "bqsr_g_count")}
     kern = {n: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                 "GBps": (v["alg_bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 and v["alg_bytes"] > 0 else None} for n, v in sorted(stats.items(), key=lambda kv: -kv[1]["ms"])}
     cpu = None
@@ -297,11 +348,16 @@ def main():
                "sample": f"first {n_s} reads of rank 0's workload, one pass; C restatement of the elPrep 5.1.3 algorithm (oracle/), not the Go binary"}
     verified = None
     if args.verify if args.verify is not None else world == 1:
+
+        ctx.reset(); ctx.append(w.batch); phases(ctx); ctx.fetch_async(out_np); ctx.fetch_wait()      # one more (untimed) pass whose outputs are checked
         verified = verify_against_oracle(ctx, w, out_np, n_reads, threads)
     line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
-            "config": {"workload": workload_name, "reads_per_gpu": n_reads, "parallelism": f"contig-group x{world}", "flush": "inputs >> L2 (re-ingested every step)"},
-            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps},
+            "config": {"workload": workload_name, "cpu_arm": f"CPU arm runs a sample: the first {args.cpu_sample} reads per step", "reads_per_gpu": n_reads, "parallelism": f"contig-group x{world}", "flush": "inputs >> L2 (re-ingested every step)"},
+            "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
+                    "how": "K steps through elp_append_batch_async / phases / elp_fetch_async with pinned host buffers, software-pipelined over two contexts (upload of step s overlaps phases + download of step s-1)",
+                    "unpipelined_ms_per_step": float(np.mean(in_ms) + np.mean(dev_ms) + np.mean(out_ms))},
+            "phases_per_rank": phases_per_rank, "roofline_graded": graded,
             "gpu_launches": launches, "verified": (verified or {}).get("ok"), "verify": verified, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": kern}
     print(json.dumps(line))
     if dist:

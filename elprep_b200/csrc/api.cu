@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of include/elprep_b200.h: context lifecycle, batch ingest, phase entry points, fetch.
 #include <algorithm>
 #include <map>
+#include <thread>
 #include "../../include/elprep_b200.h"
 #include "ctx.h"
 
@@ -184,6 +185,8 @@ void elp_destroy(elp_ctx* c) {
     for (auto& pe : c->pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
+    if (c->copy_in) { cudaStreamDestroy(c->copy_in); cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_staged); }
+    if (c->copy_out) { cudaStreamDestroy(c->copy_out); cudaEventDestroy(c->ev_out); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -191,6 +194,8 @@ void elp_destroy(elp_ctx* c) {
 int elp_reset(elp_ctx* c) {
     if (!c) return ELP_EINVAL;
     cudaSetDevice(c->device);
+    if (c->copy_in) CUDA_TRY(c, cudaStreamSynchronize(c->copy_in));
+    if (c->copy_out) CUDA_TRY(c, cudaStreamSynchronize(c->copy_out));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->n = c->n_qname = c->n_cigar = 0; c->n_qual = c->n_seq = ARENA_FRONT_PAD; c->n_bam = c->bam_reads = 0; c->n_filtered = 0;
     CUDA_TRY(c, cudaMemsetAsync(c->d_qpresent, 0, 16, c->stream));
@@ -254,8 +259,19 @@ int elp_set_known_sites(elp_ctx* c, int32_t contig, const int32_t* se, uint64_t 
 
 uint64_t elp_n_reads(const elp_ctx* c) { return c ? c->n : 0; }
 
-int elp_append_batch(elp_ctx* c, const elp_batch* b) {
-    if (!c || !b) return ELP_EINVAL;
+// elp_append_batch and its asynchronous form.  All host->device copies go to the context's ingest stream (`copy_in`), the small kernels
+// that turn batch-relative offsets into arena offsets follow on the compute stream behind an event, so a pipelined caller can overlap
+// the upload of one context with the kernels and the download of another (bench.py's e2e loop does exactly that with two contexts).
+static uint64_t sum_lengths(const int32_t* l, uint64_t n, uint64_t* seq_bytes) {
+    const unsigned nt = n > (1u << 20) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+    std::vector<uint64_t> a(nt, 0), b(nt, 0);
+    auto work = [&](unsigned t) { uint64_t x = 0, y = 0; for (uint64_t i = n * t / nt, e = n * (t + 1) / nt; i < e; i++) { const uint64_t v = (uint64_t)(uint32_t)l[i]; x += v; y += (v + 1) >> 1; } a[t] = x; b[t] = y; };
+    if (nt == 1) work(0); else { std::vector<std::thread> th; for (unsigned t = 0; t < nt; t++) th.emplace_back(work, t); for (auto& x : th) x.join(); }
+    uint64_t x = 0, y = 0; for (unsigned t = 0; t < nt; t++) { x += a[t]; y += b[t]; }
+    *seq_bytes = y; return x;
+}
+
+static int append_impl(elp_ctx* c, const elp_batch* b, bool wait) {
     cudaSetDevice(c->device);
     std::lock_guard<std::mutex> lk(c->append_mu);
     const uint64_t bn = b->n;
@@ -264,43 +280,61 @@ int elp_append_batch(elp_ctx* c, const elp_batch* b) {
     const uint64_t n0 = c->n, n1 = n0 + bn;
     if (n1 >= (1ull << 32)) return c->fail(E_LIMIT, "more than 2^32-1 reads in one context");
     const uint64_t bq = b->qname_off[bn] - b->qname_off[0], bc = b->cigar_off[bn] - b->cigar_off[0];
-    uint64_t bbases = 0, bseq = 0;
-    for (uint64_t i = 0; i < bn; i++) { const uint64_t l = (uint64_t)(uint32_t)b->l_seq[i]; bbases += l; bseq += (l + 1) >> 1; }
+    uint64_t bseq = 0;
+    const uint64_t bbases = sum_lengths(b->l_seq, bn, &bseq);
+    // growing a buffer moves it: uploads of an earlier asynchronous append that are still in flight must land first
+    if (c->copy_in && (n1 + 2 > c->flag.cap || n1 + 2 > c->qname_off.cap || c->n_qname + bq + 64 > c->qname.cap || c->n_cigar + bc + 16 > c->cigar.cap ||
+                       c->n_qual + bbases + 64 > c->qual.cap || c->n_seq + bseq + 64 > c->seq.cap)) CUDA_TRY(c, cudaStreamSynchronize(c->copy_in));
     TRY(grow(c, c->refid, n1 + 1, n0)); TRY(grow(c, c->pos, n1 + 1, n0)); TRY(grow(c, c->nref, n1 + 1, n0)); TRY(grow(c, c->pnext, n1 + 1, n0)); TRY(grow(c, c->tlen, n1 + 1, n0));
     TRY(grow(c, c->rg, n1 + 1, n0)); TRY(grow(c, c->flag, n1 + 2, n0)); TRY(grow(c, c->mapq, n1 + 1, n0));
     TRY(grow(c, c->qname_off, n1 + 2, n0 + 1)); TRY(grow(c, c->cigar_off, n1 + 2, n0 + 1)); TRY(grow(c, c->qual_off, n1 + 2, n0 + 1)); TRY(grow(c, c->seq_off, n1 + 2, n0 + 1));
     TRY(grow(c, c->qname, c->n_qname + bq + 64, c->n_qname)); TRY(grow(c, c->cigar, c->n_cigar + bc + 16, c->n_cigar));
     TRY(grow(c, c->qual, c->n_qual + bbases + 64, c->n_qual)); TRY(grow(c, c->seq, c->n_seq + bseq + 64, c->n_seq));
-    TRY(grow(c, c->off_stage, bn + 2, 0)); TRY(grow(c, c->lseq_stage, bn + 2, 0)); TRY(grow(c, c->scan_tmp, 2 * bn + 8, 0));
-    cudaStream_t s = c->stream;
+    if (!c->copy_in) { CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking)); CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_in, cudaEventDisableTiming)); CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_staged, cudaEventDisableTiming)); }
+    cudaStream_t s = c->stream, ci = c->copy_in;
+    // the staging buffers of the previous append must have been consumed by its kernels; growth (above) may also have used the compute stream
+    CUDA_TRY(c, cudaEventRecord(c->ev_staged, s)); CUDA_TRY(c, cudaStreamWaitEvent(ci, c->ev_staged, 0));
+    TRY(grow(c, c->off_stage, 2 * (bn + 2), 0)); TRY(grow(c, c->lseq_stage, bn + 2, 0)); TRY(grow(c, c->scan_tmp, 2 * bn + 8, 0));
     const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
-    CUDA_TRY(c, cudaMemcpyAsync(c->refid.p + n0, b->refid, bn * 4, H2D, s)); CUDA_TRY(c, cudaMemcpyAsync(c->pos.p + n0, b->pos, bn * 4, H2D, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->nref.p + n0, b->nref, bn * 4, H2D, s)); CUDA_TRY(c, cudaMemcpyAsync(c->pnext.p + n0, b->pnext, bn * 4, H2D, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->tlen.p + n0, b->tlen, bn * 4, H2D, s)); CUDA_TRY(c, cudaMemcpyAsync(c->rg.p + n0, b->rg, bn * 4, H2D, s));
-    CUDA_TRY(c, cudaMemcpyAsync(c->flag.p + n0, b->flag, bn * 2, H2D, s)); CUDA_TRY(c, cudaMemcpyAsync(c->mapq.p + n0, b->mapq, bn, H2D, s));
-    if (bq) CUDA_TRY(c, cudaMemcpyAsync(c->qname.p + c->n_qname, b->qname + b->qname_off[0], bq, H2D, s));
-    if (bc) CUDA_TRY(c, cudaMemcpyAsync(c->cigar.p + c->n_cigar, b->cigar + b->cigar_off[0], bc * 4, H2D, s));
-    if (bbases) CUDA_TRY(c, cudaMemcpyAsync(c->qual.p + c->n_qual, b->qual, bbases, H2D, s));
-    if (bseq) CUDA_TRY(c, cudaMemcpyAsync(c->seq.p + c->n_seq, b->seq, bseq, H2D, s));
+    CUDA_TRY(c, cudaMemcpyAsync(c->refid.p + n0, b->refid, bn * 4, H2D, ci)); CUDA_TRY(c, cudaMemcpyAsync(c->pos.p + n0, b->pos, bn * 4, H2D, ci));
+    CUDA_TRY(c, cudaMemcpyAsync(c->nref.p + n0, b->nref, bn * 4, H2D, ci)); CUDA_TRY(c, cudaMemcpyAsync(c->pnext.p + n0, b->pnext, bn * 4, H2D, ci));
+    CUDA_TRY(c, cudaMemcpyAsync(c->tlen.p + n0, b->tlen, bn * 4, H2D, ci)); CUDA_TRY(c, cudaMemcpyAsync(c->rg.p + n0, b->rg, bn * 4, H2D, ci));
+    CUDA_TRY(c, cudaMemcpyAsync(c->flag.p + n0, b->flag, bn * 2, H2D, ci)); CUDA_TRY(c, cudaMemcpyAsync(c->mapq.p + n0, b->mapq, bn, H2D, ci));
+    uint64_t* st_q = c->off_stage.p; uint64_t* st_c = c->off_stage.p + (bn + 2);
+    CUDA_TRY(c, cudaMemcpyAsync(st_q, b->qname_off, (bn + 1) * 8, H2D, ci));
+    CUDA_TRY(c, cudaMemcpyAsync(st_c, b->cigar_off, (bn + 1) * 8, H2D, ci));
+    CUDA_TRY(c, cudaMemcpyAsync(c->lseq_stage.p, b->l_seq, bn * 4, H2D, ci));
+    if (bq) CUDA_TRY(c, cudaMemcpyAsync(c->qname.p + c->n_qname, b->qname + b->qname_off[0], bq, H2D, ci));
+    if (bc) CUDA_TRY(c, cudaMemcpyAsync(c->cigar.p + c->n_cigar, b->cigar + b->cigar_off[0], bc * 4, H2D, ci));
+    if (bseq) CUDA_TRY(c, cudaMemcpyAsync(c->seq.p + c->n_seq, b->seq, bseq, H2D, ci));
+    if (bbases) CUDA_TRY(c, cudaMemcpyAsync(c->qual.p + c->n_qual, b->qual, bbases, H2D, ci));
+    CUDA_TRY(c, cudaEventRecord(c->ev_in, ci));
+    CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_in, 0));
     // offsets: batch-relative -> arena-global
-    CUDA_TRY(c, cudaMemcpyAsync(c->off_stage.p, b->qname_off, (bn + 1) * 8, H2D, s));
-    rebase_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->off_stage.p, c->n_qname - b->qname_off[0], c->qname_off.p + n0); c->launches++;
-    CUDA_TRY(c, cudaStreamSynchronize(s));   // off_stage is reused below
-    CUDA_TRY(c, cudaMemcpyAsync(c->off_stage.p, b->cigar_off, (bn + 1) * 8, H2D, s));
-    rebase_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->off_stage.p, c->n_cigar - b->cigar_off[0], c->cigar_off.p + n0); c->launches++;
-    CUDA_TRY(c, cudaMemcpyAsync(c->lseq_stage.p, b->l_seq, bn * 4, H2D, s));
+    rebase_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, st_q, c->n_qname - b->qname_off[0], c->qname_off.p + n0); c->launches++;
+    rebase_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, st_c, c->n_cigar - b->cigar_off[0], c->cigar_off.p + n0); c->launches++;
     uint32_t* qlen = c->scan_tmp.p; uint32_t* slen = c->scan_tmp.p + bn + 4;
     lens_kernel<<<nblk(bn, 256), 256, 0, s>>>(bn, c->lseq_stage.p, qlen, slen); c->launches++;
     LAUNCH_CHECK(c);
     TRY(exclusive_scan_u32_to_u64(c, qlen, c->qual_off.p + n0, bn));
-    if (c->n_qual) { add_base_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->qual_off.p + n0, c->n_qual); c->launches++; }
-    TRY(qual_presence_update(c, c->n_qual, bbases));
+    add_base_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->qual_off.p + n0, c->n_qual); c->launches++;
     TRY(exclusive_scan_u32_to_u64(c, slen, c->seq_off.p + n0, bn));
-    if (c->n_seq) { add_base_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->seq_off.p + n0, c->n_seq); c->launches++; }
+    add_base_kernel<<<nblk(bn + 1, 256), 256, 0, s>>>(bn + 1, c->seq_off.p + n0, c->n_seq); c->launches++;
     LAUNCH_CHECK(c);
-    CUDA_TRY(c, cudaStreamSynchronize(s));   // the caller's buffers may be released after return (cgo pointer rules)
+    TRY(qual_presence_update(c, c->n_qual, bbases));
     c->n = n1; c->n_qname += bq; c->n_cigar += bc; c->n_qual += bbases; c->n_seq += bseq;
     c->adapted = false;
+    if (wait) { CUDA_TRY(c, cudaStreamSynchronize(ci)); CUDA_TRY(c, cudaStreamSynchronize(s)); }   // the caller's buffers may be released after return (cgo pointer rules)
+    return ELP_OK;
+}
+
+int elp_append_batch(elp_ctx* c, const elp_batch* b) { if (!c || !b) return ELP_EINVAL; return append_impl(c, b, true); }
+int elp_append_batch_async(elp_ctx* c, const elp_batch* b) { if (!c || !b) return ELP_EINVAL; return append_impl(c, b, false); }
+int elp_append_wait(elp_ctx* c) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (c->copy_in) CUDA_TRY(c, cudaStreamSynchronize(c->copy_in));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return ELP_OK;
 }
 
@@ -364,35 +398,51 @@ uint64_t elp_fetch_qual_bytes(elp_ctx* c, uint64_t first, uint64_t n) {
     return v[1] - v[0];
 }
 
-int elp_fetch(elp_ctx* c, uint64_t first, uint64_t n, uint64_t* record_index, uint16_t* flag, uint64_t* qual_off, uint8_t* qual, uint64_t qual_capacity) {
-    if (!c) return ELP_EINVAL;
+static int fetch_impl(elp_ctx* c, uint64_t first, uint64_t n, uint64_t* record_index, uint32_t* record_index32, uint16_t* flag, uint64_t* qual_off, uint8_t* qual, uint64_t qual_capacity, bool wait) {
     cudaSetDevice(c->device);
     if (!c->sorted) return c->fail(E_STATE, "elp_fetch before elp_sort_markdup");
     if (first + n > c->n) return c->fail(E_INVAL, "elp_fetch: range [%llu,%llu) exceeds %llu reads", (unsigned long long)first, (unsigned long long)(first + n), (unsigned long long)c->n);
     if (n == 0) { if (qual_off) qual_off[0] = 0; return ELP_OK; }
     cudaStream_t s = c->stream;
-    if (record_index) {
-        TRY(grow(c, c->off_stage, n + 2, 0));
-        widen_kernel<<<nblk(n, 256), 256, 0, s>>>(n, c->perm.p + first, c->off_stage.p); c->launches++;
-        CUDA_TRY(c, cudaMemcpyAsync(record_index, c->off_stage.p, n * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(c, cudaStreamSynchronize(s));
-    }
-    if (flag) CUDA_TRY(c, cudaMemcpyAsync(flag, c->s_flag.p + first, n * 2, cudaMemcpyDeviceToHost, s));
-    if (qual_off) {
-        TRY(grow(c, c->off_stage, n + 2, 0));
-        rel_off_kernel<<<nblk(n + 1, 256), 256, 0, s>>>(n, c->s_out_off.p, first, c->off_stage.p); c->launches++;
-        CUDA_TRY(c, cudaMemcpyAsync(qual_off, c->off_stage.p, (n + 1) * 8, cudaMemcpyDeviceToHost, s));
-    }
+    if (!c->copy_out) { CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking)); CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming)); }
+    cudaStream_t co = c->copy_out;
+    uint64_t v[2] = {0, 0};
     if (qual) {
         if (!c->qual_out_valid) TRY(run_apply_kernel(c, false));   // no BQSR: just the QUAL bytes in output order
-        uint64_t v[2];
-        CUDA_TRY(c, cudaMemcpyAsync(&v[0], c->s_out_off.p + first, 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(c, cudaMemcpyAsync(&v[1], c->s_out_off.p + first + n, 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(c, cudaStreamSynchronize(s));
+        if (first == 0 && n == c->n) { v[0] = 0; v[1] = c->qual_out_total; }
+        else {
+            CUDA_TRY(c, cudaMemcpyAsync(&v[0], c->s_out_off.p + first, 8, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(c, cudaMemcpyAsync(&v[1], c->s_out_off.p + first + n, 8, cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(c, cudaStreamSynchronize(s));
+        }
         if (v[1] - v[0] > qual_capacity) return c->fail(E_INVAL, "elp_fetch: qual buffer too small (%llu > %llu)", (unsigned long long)(v[1] - v[0]), (unsigned long long)qual_capacity);
-        CUDA_TRY(c, cudaMemcpyAsync(qual, c->qual_out.p + v[0], v[1] - v[0], cudaMemcpyDeviceToHost, s));
     }
-    CUDA_TRY(c, cudaStreamSynchronize(s));
+    if (record_index || qual_off) TRY(grow(c, c->off_stage, 2 * (n + 2), 0));
+    if (record_index) { widen_kernel<<<nblk(n, 256), 256, 0, s>>>(n, c->perm.p + first, c->off_stage.p); c->launches++; }
+    if (qual_off) { rel_off_kernel<<<nblk(n + 1, 256), 256, 0, s>>>(n, c->s_out_off.p, first, c->off_stage.p + (n + 2)); c->launches++; }
+    LAUNCH_CHECK(c);
+    // everything the compute stream produced so far (apply, the two small kernels above) -> the download stream
+    CUDA_TRY(c, cudaEventRecord(c->ev_out, s)); CUDA_TRY(c, cudaStreamWaitEvent(co, c->ev_out, 0));
+    if (qual) CUDA_TRY(c, cudaMemcpyAsync(qual, c->qual_out.p + v[0], v[1] - v[0], cudaMemcpyDeviceToHost, co));
+    if (record_index) CUDA_TRY(c, cudaMemcpyAsync(record_index, c->off_stage.p, n * 8, cudaMemcpyDeviceToHost, co));
+    if (record_index32) CUDA_TRY(c, cudaMemcpyAsync(record_index32, c->perm.p + first, n * 4, cudaMemcpyDeviceToHost, co));
+    if (flag) CUDA_TRY(c, cudaMemcpyAsync(flag, c->s_flag.p + first, n * 2, cudaMemcpyDeviceToHost, co));
+    if (qual_off) CUDA_TRY(c, cudaMemcpyAsync(qual_off, c->off_stage.p + (n + 2), (n + 1) * 8, cudaMemcpyDeviceToHost, co));
+    if (wait) CUDA_TRY(c, cudaStreamSynchronize(co));
+    return ELP_OK;
+}
+int elp_fetch(elp_ctx* c, uint64_t first, uint64_t n, uint64_t* record_index, uint16_t* flag, uint64_t* qual_off, uint8_t* qual, uint64_t qual_capacity) {
+    if (!c) return ELP_EINVAL;
+    return fetch_impl(c, first, n, record_index, nullptr, flag, qual_off, qual, qual_capacity, true);
+}
+int elp_fetch_async(elp_ctx* c, uint64_t first, uint64_t n, uint32_t* record_index32, uint16_t* flag, uint64_t* qual_off, uint8_t* qual, uint64_t qual_capacity) {
+    if (!c) return ELP_EINVAL;
+    return fetch_impl(c, first, n, nullptr, record_index32, flag, qual_off, qual, qual_capacity, false);
+}
+int elp_fetch_wait(elp_ctx* c) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (c->copy_out) CUDA_TRY(c, cudaStreamSynchronize(c->copy_out));
     return ELP_OK;
 }
 

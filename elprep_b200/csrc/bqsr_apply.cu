@@ -164,6 +164,7 @@ int run_apply_kernel(elp_ctx* c, bool with_lut) {
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     }
     CUDA_TRY(c, c->qual_out.reserve(total + 64, c->stream));
+    c->qual_out_total = total;
     if (n) {
         static bool tables_set[64] = {false};
         if (!tables_set[c->device & 63]) {

@@ -151,6 +151,7 @@ struct CountArgs {
     const uint4* recs; const uint4* segs; const uint32_t* n_seg; uint32_t* seg_next;
     unsigned long long* tables; TableGeom geom;
     int lpr, rpw; uint32_t sh, lut_lo, lut_hi; uint8_t slot_q[4];
+    uint32_t rec_bytes;             // ring slot of one pass' records: 32 * rpw
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_shared, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory"); }
@@ -160,8 +161,8 @@ __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long
 template <int S, bool INDEL>
 __global__ void __launch_bounds__(CNT_WARPS * 32, 2) bqsr_count_kernel(CountArgs A) {
     constexpr int NCH = INDEL ? 9 : 7;                                  // 16-byte chunks per lane and pass: QUAL 3, SEQ 2, REF 2 (+2)
-    constexpr int STAGE_BYTES = NCH * 512, REC_BYTES = 256;             // per warp
-    constexpr int WARP_BYTES = CNT_STAGES * STAGE_BYTES + CNT_RECRING * REC_BYTES;
+    constexpr int STAGE_BYTES = NCH * 512;                              // per warp
+    const uint32_t REC_BYTES = A.rec_bytes, WARP_BYTES = CNT_STAGES * STAGE_BYTES + CNT_RECRING * REC_BYTES;
     extern __shared__ __align__(16) unsigned char cnt_smem[];
     __shared__ uint32_t s_rt[33];
     if (threadIdx.x < 33) s_rt[threadIdx.x] = lanes::range_plane((int)threadIdx.x);
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(CNT_WARPS * 32, 2) bqsr_count_kernel(CountArgs
             // ---- (a) records of pass `it` -> ring slot it % 6 ----
             if (it < n_pass) {
                 const uint32_t nrec_here = min((uint32_t)rpw, n_rec - (uint32_t)it * (uint32_t)rpw);
-                if (lane < 2 * nrec_here) cp_async16(rbase + (uint32_t)(it % CNT_RECRING) * REC_BYTES + lane * 16u, A.recs + 2 * ((uint64_t)rec_first + (uint64_t)it * rpw) + lane);
+                for (uint32_t x = lane; x < 2 * nrec_here; x += 32) cp_async16(rbase + (uint32_t)(it % CNT_RECRING) * REC_BYTES + x * 16u, A.recs + 2 * ((uint64_t)rec_first + (uint64_t)it * rpw) + x);
             }
             // ---- (b) QUAL / SEQ / reference windows of pass it - 3 -> stage (it - 3) % 3 ----
             const int pd = it - 3;

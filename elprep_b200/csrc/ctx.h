@@ -55,6 +55,8 @@ struct TableGeom {
 struct elp_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // upload / download streams of the asynchronous append / fetch
+    cudaEvent_t ev_in = nullptr, ev_staged = nullptr, ev_out = nullptr;
     std::string err;
     std::mutex append_mu;
     bool profile = false;
@@ -135,6 +137,7 @@ struct elp_ctx {
     DBuf<uint32_t> s_ncigar;
     DBuf<uint8_t> qual_out;                   // recalibrated QUAL in output order
     bool qual_out_valid = false;
+    uint64_t qual_out_total = 0;              // bytes of the output QUAL stream
 
     // ---- BQSR ----
     TableGeom geom;

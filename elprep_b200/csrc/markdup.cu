@@ -14,6 +14,7 @@
 // outcome equals a single goroutine processing reads in arrival order (the later read/pair survives, :231-238,380-386).
 #include "ctx.h"
 #include <climits>
+#include <algorithm>
 
 namespace {
 
@@ -25,110 +26,175 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 }
 
 // ---------------------------------------------------------------- K1 adapt
-// 8 lanes per read (4 reads per warp); QUAL strips are read as aligned 16-byte chunks with byte masks.
-#ifndef ADAPT_MINB
-#define ADAPT_MINB 5
-#endif
-__global__ void __launch_bounds__(256, ADAPT_MINB) adapt_kernel(uint64_t n, const uint16_t* __restrict__ flag, const int32_t* __restrict__ pos,
-                                                     const int32_t* __restrict__ rg, const int32_t* __restrict__ rg_lib, int n_rg,
-                                                     const uint64_t* __restrict__ cigar_off, const uint32_t* __restrict__ cigar,
-                                                     const uint64_t* __restrict__ qual_off, const uint8_t* __restrict__ qual,
-                                                     const uint64_t* __restrict__ qname_off, const uint8_t* __restrict__ qname,
-                                                     int32_t* __restrict__ upos_out, int32_t* __restrict__ score_out, uint64_t* __restrict__ qhash_out,
-                                                     DeviceRanges* __restrict__ ranges, uint32_t* __restrict__ err) {
-    const unsigned lane = lane_id(), sub = lane & 7, grp = lane >> 3;
-    const uint64_t gw = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint64_t nw = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+// adaptAlignment (mark-duplicates.go:153-156) for every read, one THREAD per read over tiles of consecutive reads.  The reads of a tile
+// are consecutive in the QUAL, QNAME and CIGAR arenas (arrival order), so a tile's three byte strips are fetched with one TMA bulk copy
+// each (cp.async.bulk, mbarrier-completed) into a four-deep shared-memory ring; the threads then read their read's bytes out of shared
+// memory word by word (masked SWAR compares + __dp4a for the phred sum, a position-salted word mix for the (library, QNAME) hash).
+// A tile whose strips do not fit its ring slot (very long reads) takes the same code with global loads.
+constexpr int AD_T = 256, AD_STAGES = 4;
+constexpr uint32_t AD_QCAP = 39 * 1024, AD_NCAP = 9 * 1024, AD_CCAP = 3 * 1024, AD_STAGE = AD_QCAP + AD_NCAP + AD_CCAP;
+
+struct AdaptArgs {
+    uint64_t n; int reads_per_tile;
+    const uint16_t* flag; const int32_t *pos, *rg, *rg_lib; int n_rg;
+    const uint64_t* cigar_off; const uint32_t* cigar; const uint64_t* qual_off; const uint8_t* qual; const uint64_t* qname_off; const uint8_t* qname;
+    int32_t *upos, *score; uint64_t* qhash; DeviceRanges* ranges; uint32_t* err;
+};
+
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{\n .reg .pred P1;\n AD_WAIT:\n mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n @P1 bra AD_DONE;\n bra AD_WAIT;\n AD_DONE:\n }" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (16-byte aligned addresses and size)
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// word-granular byte-strip access: STAGED reads shared memory at (base + byte offset), otherwise global memory
+template <bool STAGED> struct Strip {
+    uint32_t sbase; const uint8_t* gbase;     // address of arena byte `origin` in shared memory / the arena itself
+    uint64_t origin;
+    __device__ __forceinline__ uint32_t word(uint64_t aligned_byte) const {     // 4-byte aligned arena offset
+        if (STAGED) return lds32(sbase + (uint32_t)(aligned_byte - origin));
+        return __ldg(reinterpret_cast<const uint32_t*>(gbase + aligned_byte));
+    }
+};
+
+// computePhredScore (:57-68): sum over QUAL >= 15 of (q & 0x7f) (the table index byte(char << 1) wraps), bad: some byte > 93
+template <bool STAGED> __device__ __forceinline__ uint32_t phred_score(const Strip<STAGED>& Q, uint64_t q0, uint64_t q1, unsigned lane, uint32_t& bad) {
+    if (q1 <= q0) return 0;
+    const uint64_t w0 = q0 & ~3ull;
+    const uint32_t nw = (uint32_t)((((q1 - 1) & ~3ull) - w0) >> 2) + 1;
+    const uint32_t first_mask = 0xffffffffu << (8 * (uint32_t)(q0 & 3)), last_mask = 0xffffffffu >> (8 * (3 - (uint32_t)((q1 - 1) & 3)));
+    uint32_t s = 0;
+    uint32_t k = lane % nw;                        // lanes start at different words: no shared-memory bank pile-up for power-of-two read lengths
+    for (uint32_t t = 0; t < nw; t++) {
+        uint32_t m = 0x7f7f7f7fu;
+        if (k == 0) m &= first_mask;
+        if (k == nw - 1) m &= last_mask;
+        const uint32_t x = Q.word(w0 + 4ull * k) & m;            // bytes < 128: the adds below cannot carry across bytes
+        bad |= (x + 0x22222222u) & 0x80808080u;
+        const uint32_t ge15 = ((x + 0x71717171u) & 0x80808080u) >> 7;
+        s = __dp4a(x & (ge15 * 0xffu), 0x01010101u, s);
+        k = (k + 1 == nw) ? 0 : k + 1;
+    }
+    return s;
+}
+// (library, QNAME) hash for the mate join: a function of the name bytes only (equality is verified on bytes in join_kernel)
+template <bool STAGED> __device__ __forceinline__ uint64_t qname_hash(const Strip<STAGED>& N, uint64_t n0, uint64_t n1) {
+    uint64_t h = 0;
+    if (n1 <= n0) return h;
+    const uint32_t sh = 8 * (uint32_t)(n0 & 3);
+    uint64_t a = n0 & ~3ull;
+    uint32_t lo = N.word(a);
+    for (uint64_t k = n0; k < n1; k += 4) {
+        const uint32_t hi = (a + 4 < n1) ? N.word(a + 4) : 0u;   // only fetched when the name continues into the next word
+        uint32_t wv = __funnelshift_r(lo, hi, sh);
+        const uint32_t rem = (uint32_t)(n1 - k);
+        if (rem < 4) wv &= 0xffffffffu >> (8 * (4 - rem));
+        uint32_t m = (wv ^ ((uint32_t)(k - n0) * 0x9E3779B1u)) * 0x85EBCA6Bu;
+        m ^= m >> 15; m *= 0xC2B2AE35u; m ^= m >> 13;
+        h += (uint64_t)m * 0x9E3779B97F4A7C15ull;
+        lo = hi; a += 4;
+    }
+    return h;
+}
+// computeUnclippedPosition (:79-110)
+template <bool STAGED> __device__ __forceinline__ int32_t unclipped_pos(const Strip<STAGED>& C, uint64_t c0, uint64_t c1, int32_t p, bool reversed) {
+    int32_t up = p;
+    if (c1 <= c0) return up;
+    if (reversed) {
+        int32_t clipped = 1; up--;
+        for (uint64_t k = c1; k-- > c0;) {
+            const uint32_t op = C.word(4 * k); const uint32_t o = op & 15; const int32_t l = (int32_t)(op >> 4);
+            const int32_t cl = (o == 4 || o == 5), r = (o == 0 || o == 2 || o == 3 || o == 7 || o == 8);
+            clipped *= cl;
+            up += (r | clipped) * l;
+        }
+    } else {
+        for (uint64_t k = c0; k < c1; k++) { const uint32_t op = C.word(4 * k); const uint32_t o = op & 15; if (!(o == 4 || o == 5)) break; up -= (int32_t)(op >> 4); }
+    }
+    return up;
+}
+
+struct AdTile { uint64_t qb, nb, cb; uint32_t staged; };   // arena offsets of the first staged byte of each strip
+
+__global__ void __launch_bounds__(AD_T, 1) adapt_kernel(AdaptArgs A) {
+    extern __shared__ __align__(128) unsigned char ad_smem[];
+    __shared__ __align__(8) uint64_t bars[AD_STAGES];
+    __shared__ AdTile tinfo[AD_STAGES];
+    const unsigned tid = threadIdx.x, lane = tid & 31;
+    const uint32_t sm0 = (uint32_t)__cvta_generic_to_shared(ad_smem), bar0 = (uint32_t)__cvta_generic_to_shared(bars);
+    const uint64_t R = (uint64_t)A.reads_per_tile, n_tiles = (A.n + R - 1) / R;
+    if (tid == 0) { for (int s = 0; s < AD_STAGES; s++) mbar_init(bar0 + 8 * s, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    // thread 0: strips of tile t -> ring slot `slot`
+    auto issue = [&](uint64_t t, int slot) {
+        const uint64_t i0 = t * R, i1 = min(A.n, i0 + R);
+        const uint64_t qa = A.qual_off[i0], qe = A.qual_off[i1], na = A.qname_off[i0], ne = A.qname_off[i1], ca = A.cigar_off[i0] * 4, ce = A.cigar_off[i1] * 4;
+        const uintptr_t gq = reinterpret_cast<uintptr_t>(A.qual), gn = reinterpret_cast<uintptr_t>(A.qname), gc = reinterpret_cast<uintptr_t>(A.cigar);
+        // windows aligned on 16-byte ADDRESSES (the arenas themselves are 256-byte aligned, so offsets and addresses agree mod 16)
+        const uint64_t qb = qa & ~15ull, nb = na & ~15ull, cb = ca & ~15ull;
+        const uint64_t qs = ((qe + 15) & ~15ull) - qb, ns = ((ne + 15) & ~15ull) - nb, cs = ((ce + 15) & ~15ull) - cb;
+        const bool fits = qs <= AD_QCAP && ns <= AD_NCAP && cs <= AD_CCAP && ((gq | gn | gc) & 15) == 0;
+        AdTile ti; ti.qb = qb; ti.nb = nb; ti.cb = cb; ti.staged = fits ? 1u : 0u;
+        tinfo[slot] = ti;
+        const uint32_t bar = bar0 + 8 * slot, dst = sm0 + (uint32_t)slot * AD_STAGE;
+        if (fits) {
+            mbar_expect_tx(bar, (uint32_t)(qs + ns + cs));
+            if (qs) bulk_g2s(dst, A.qual + qb, (uint32_t)qs, bar);
+            if (ns) bulk_g2s(dst + AD_QCAP, A.qname + nb, (uint32_t)ns, bar);
+            if (cs) bulk_g2s(dst + AD_QCAP + AD_NCAP, reinterpret_cast<const uint8_t*>(A.cigar) + cb, (uint32_t)cs, bar);
+        } else mbar_arrive(bar);
+    };
+    if (tid == 0) for (int s = 0; s < AD_STAGES - 1; s++) { const uint64_t t = (uint64_t)blockIdx.x + (uint64_t)s * gridDim.x; if (t < n_tiles) issue(t, s); }
+    __syncthreads();
+
     int32_t pos_max = 0, upos_min = INT_MAX, upos_max = INT_MIN, score_max = 0, lseq_max = 0, pos_min = 0, qname_max = 0;
     uint32_t n_enter = 0, n_pairs = 0, errbits = 0;
-    for (uint64_t i0 = gw * 4; i0 < n; i0 += nw * 4) {
-        const uint64_t i = i0 + grp;
-        const bool valid = i < n;
-        uint16_t f = 0; int32_t p = 0; uint64_t q0 = 0, q1 = 0;
-        if (valid) { f = flag[i]; p = pos[i]; q0 = qual_off[i]; q1 = qual_off[i + 1]; qname_max = max(qname_max, (int32_t)(qname_off[i + 1] - qname_off[i])); }
-        const int32_t len = (int32_t)(q1 - q0);
-        pos_max = max(pos_max, p); pos_min = min(pos_min, p); lseq_max = max(lseq_max, len);
-        const bool entering = valid && (f & (F_UNMAPPED | F_SECONDARY | F_SUPPLEMENTARY)) == 0;   // mark-duplicates.go:436
-        int32_t up = 0, sc = 0; uint64_t qh = 0;
-        uint32_t s = 0, bad = 0; uint64_t h = 0;
-        const bool true_pair = entering && (f & (F_MULTIPLE | F_NEXTUNMAPPED)) == F_MULTIPLE;   // :182-184
-        if (entering) {
-            // computeUnclippedPosition (:79-110), serial over the (short) CIGAR on the group's first lane
-            if (sub == 0) {
-                const uint64_t c0 = cigar_off[i], c1 = cigar_off[i + 1];
-                up = p;
-                if (c1 > c0) {
-                    if (f & F_REVERSED) {
-                        int32_t clipped = 1; up--;
-                        for (uint64_t k = c1; k-- > c0;) {
-                            const uint32_t op = cigar[k]; const uint32_t o = op & 15; const int32_t l = (int32_t)(op >> 4);
-                            const int32_t cl = (o == 4 || o == 5), r = (o == 0 || o == 2 || o == 3 || o == 7 || o == 8);
-                            clipped *= cl;
-                            up += (r | clipped) * l;
-                        }
-                    } else {
-                        for (uint64_t k = c0; k < c1; k++) { const uint32_t op = cigar[k]; const uint32_t o = op & 15; if (!(o == 4 || o == 5)) break; up -= (int32_t)(op >> 4); }
-                    }
+    uint64_t it = 0;
+    for (uint64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+        const int slot = (int)(it % AD_STAGES);
+        // refill the slot that was consumed in the previous iteration (all threads passed its trailing __syncthreads)
+        if (tid == 0) { const uint64_t tn = t + (uint64_t)(AD_STAGES - 1) * gridDim.x; if (tn < n_tiles) issue(tn, (int)((it + AD_STAGES - 1) % AD_STAGES)); }
+        const uint64_t i = t * R + tid;
+        const bool valid = tid < R && i < A.n;
+        uint16_t f = 0; int32_t p = 0; uint64_t q0 = 0, q1 = 0, n0 = 0, n1 = 0, c0 = 0, c1 = 0; int32_t g = -1;
+        if (valid) { f = A.flag[i]; p = A.pos[i]; q0 = A.qual_off[i]; q1 = A.qual_off[i + 1]; n0 = A.qname_off[i]; n1 = A.qname_off[i + 1]; c0 = A.cigar_off[i]; c1 = A.cigar_off[i + 1]; g = A.rg[i]; }
+        mbar_wait(bar0 + 8 * slot, (uint32_t)((it / AD_STAGES) & 1));
+        const AdTile ti = tinfo[slot];
+        if (valid) {
+            const int32_t len = (int32_t)(q1 - q0);
+            qname_max = max(qname_max, (int32_t)(n1 - n0));
+            pos_max = max(pos_max, p); pos_min = min(pos_min, p); lseq_max = max(lseq_max, len);
+            const bool entering = (f & (F_UNMAPPED | F_SECONDARY | F_SUPPLEMENTARY)) == 0;          // mark-duplicates.go:436
+            const bool true_pair = entering && (f & (F_MULTIPLE | F_NEXTUNMAPPED)) == F_MULTIPLE;   // :182-184
+            int32_t up = 0, sc = 0; uint64_t qh = 0;
+            if (entering) {
+                uint32_t bad = 0; uint64_t h = 0;
+                const uint32_t sbase = sm0 + (uint32_t)slot * AD_STAGE;
+                if (ti.staged) {
+                    const Strip<true> Q{sbase, nullptr, ti.qb}, N{sbase + AD_QCAP, nullptr, ti.nb}, C{sbase + AD_QCAP + AD_NCAP, nullptr, ti.cb};
+                    sc = (int32_t)phred_score(Q, q0, q1, lane, bad);
+                    up = unclipped_pos(C, c0, c1, p, (f & F_REVERSED) != 0);
+                    if (true_pair) h = qname_hash(N, n0, n1);
+                } else {
+                    const Strip<false> Q{0, A.qual, 0}, N{0, A.qname, 0}, C{0, reinterpret_cast<const uint8_t*>(A.cigar), 0};
+                    sc = (int32_t)phred_score(Q, q0, q1, lane, bad);
+                    up = unclipped_pos(C, c0, c1, p, (f & F_REVERSED) != 0);
+                    if (true_pair) h = qname_hash(N, n0, n1);
                 }
-            }
-            // computePhredScore (:57-68): sum of q>=15 over (q & 0x7f) (the table index byte(char<<1) wraps), error if >93
-            const uint64_t abase = q0 & ~15ull;
-            const uint32_t nch = (uint32_t)((((q1 + 15) & ~15ull) - abase) >> 4);
-            for (uint32_t c = sub; c < nch; c += 8) {
-                const uint64_t a = abase + 16ull * c;
-                const uint4 v = ld_stream_u4(qual + a);
-                const int lo = (int)(q0 > a ? q0 - a : 0), hi = (int)((q1 < a + 16 ? q1 : a + 16) - a);
-                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                if (lo == 0 && hi == 16) {          // interior chunk: no byte masks
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const uint32_t x = w[t] & 0x7f7f7f7fu;
-                        bad |= (x + 0x22222222u) & 0x80808080u;
-                        const uint32_t ge15 = ((x + 0x71717171u) & 0x80808080u) >> 7;
-                        s = __dp4a(x & (ge15 * 0xffu), 0x01010101u, s);
-                    }
-                    continue;
-                }
-#pragma unroll
-                for (int t = 0; t < 4; t++) {
-                    int wlo = lo - 4 * t, whi = hi - 4 * t;
-                    wlo = wlo < 0 ? 0 : (wlo > 4 ? 4 : wlo); whi = whi < 0 ? 0 : (whi > 4 ? 4 : whi);
-                    if (whi <= wlo) continue;
-                    const uint32_t mhi = whi == 4 ? 0xffffffffu : ((1u << (8 * whi)) - 1), mlo = wlo == 0 ? 0u : ((1u << (8 * wlo)) - 1);
-                    const uint32_t x = w[t] & 0x7f7f7f7fu & mhi & ~mlo;                 // bytes < 128: the adds below cannot carry across bytes
-                    bad |= (x + 0x22222222u) & 0x80808080u;                               // some byte > 93
-                    const uint32_t ge15 = ((x + 0x71717171u) & 0x80808080u) >> 7;         // 1 per byte >= 15
-                    s = __dp4a(x & (ge15 * 0xffu), 0x01010101u, s);
-                }
-            }
-            // (lib, QNAME) hash for the mate join -- only needs to be a function of the bytes; equality is verified on bytes
-            if (true_pair) {
-                const uint64_t n0 = qname_off[i], n1 = qname_off[i + 1];
-                // four bytes per step and lane; position-salted 32-bit mixes summed in 64 bits (order independent across lanes)
-                for (uint64_t k = n0 + 4 * sub; k < n1; k += 32) {
-                    uint32_t wv = 0;
-#pragma unroll
-                    for (int t = 0; t < 4; t++) if (k + t < n1) wv |= (uint32_t)qname[k + t] << (8 * t);
-                    uint32_t m = (wv ^ ((uint32_t)(k - n0) * 0x9E3779B1u)) * 0x85EBCA6Bu;
-                    m ^= m >> 15; m *= 0xC2B2AE35u; m ^= m >> 13;
-                    h += (uint64_t)m * 0x9E3779B97F4A7C15ull;
-                }
-            }
-        }
-        // reduce over the 8 lanes of the group (all lanes of the warp take part)
-#pragma unroll
-        for (int o = 4; o; o >>= 1) { s += __shfl_xor_sync(FULL_MASK, s, o); bad |= __shfl_xor_sync(FULL_MASK, bad, o); h += __shfl_xor_sync(FULL_MASK, h, o); }
-        if (entering) {
-            sc = (int32_t)s;
-            if (bad) errbits |= DERR_QUAL;
-            if (sub == 0) {
-                const int32_t g = rg[i];
-                const int32_t lib = (g >= 0 && g < n_rg) ? rg_lib[g] : -1;
-                if (true_pair) { qh = mix64(h + (uint64_t)(uint32_t)(lib + 1) * 0x9E3779B97F4A7C15ull + (qname_off[i + 1] - qname_off[i])); n_pairs++; }
+                if (bad) errbits |= DERR_QUAL;
+                const int32_t lib = (g >= 0 && g < A.n_rg) ? A.rg_lib[g] : -1;
+                if (true_pair) { qh = mix64(h + (uint64_t)(uint32_t)(lib + 1) * 0x9E3779B97F4A7C15ull + (n1 - n0)); n_pairs++; }
                 upos_min = min(upos_min, up); upos_max = max(upos_max, up); score_max = max(score_max, sc); n_enter++;
             }
+            A.upos[i] = up; A.score[i] = sc; A.qhash[i] = qh;
         }
-        if (valid && sub == 0) { upos_out[i] = up; score_out[i] = sc; qhash_out[i] = qh; }
+        __syncthreads();
     }
     // block reduction of the ranges, then one atomic per block
     __shared__ int32_t sh_i[8][7];
@@ -149,11 +215,11 @@ __global__ void __launch_bounds__(256, ADAPT_MINB) adapt_kernel(uint64_t n, cons
             sh_i[0][3] = max(sh_i[0][3], sh_i[k][3]); sh_i[0][4] = max(sh_i[0][4], sh_i[k][4]); sh_i[0][5] = min(sh_i[0][5], sh_i[k][5]); sh_i[0][6] = max(sh_i[0][6], sh_i[k][6]);
             sh_u[0][0] += sh_u[k][0]; sh_u[0][1] += sh_u[k][1]; sh_u[0][2] |= sh_u[k][2];
         }
-        atomicMax(&ranges->pos_max, sh_i[0][0]); atomicMin(&ranges->upos_min, sh_i[0][1]); atomicMax(&ranges->upos_max, sh_i[0][2]);
-        atomicMax(&ranges->score_max, sh_i[0][3]); atomicMax(&ranges->lseq_max, sh_i[0][4]); atomicMax(&ranges->qname_max, sh_i[0][6]);
-        atomicAdd(&ranges->n_entering, sh_u[0][0]); atomicAdd(&ranges->n_true_pairs, sh_u[0][1]);
+        atomicMax(&A.ranges->pos_max, sh_i[0][0]); atomicMin(&A.ranges->upos_min, sh_i[0][1]); atomicMax(&A.ranges->upos_max, sh_i[0][2]);
+        atomicMax(&A.ranges->score_max, sh_i[0][3]); atomicMax(&A.ranges->lseq_max, sh_i[0][4]); atomicMax(&A.ranges->qname_max, sh_i[0][6]);
+        atomicAdd(&A.ranges->n_entering, sh_u[0][0]); atomicAdd(&A.ranges->n_true_pairs, sh_u[0][1]);
         if (sh_i[0][5] < 0) sh_u[0][2] |= DERR_QUAL_RANGE;   // negative POS: not representable in the compact sort key
-        if (sh_u[0][2]) atomicOr(err, sh_u[0][2]);
+        if (sh_u[0][2]) atomicOr(A.err, sh_u[0][2]);
     }
 }
 
@@ -357,12 +423,21 @@ int phase_adapt(elp_ctx* c) {
     CUDA_TRY(c, cudaMemcpyAsync(c->d_ranges, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     if (n) {
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-        uint64_t want = (n / 4 * 32 + 255) / 256;
-        unsigned grid = (unsigned)std::min<uint64_t>(std::max<uint64_t>(want, 1), (uint64_t)sms * 8);
-        double bytes = (double)n * (2 + 4 + 4 + 16 + 16 + 8 + 4 + 4 + 8) + (double)c->n_qual + (double)c->n_cigar * 4 + (double)c->n_qname;
+        AdaptArgs A{};
+        A.n = n; A.flag = c->flag.p; A.pos = c->pos.p; A.rg = c->rg.p; A.rg_lib = c->d_rg_lib; A.n_rg = c->n_rg; A.cigar_off = c->cigar_off.p; A.cigar = c->cigar.p;
+        A.qual_off = c->qual_off.p; A.qual = c->qual.p; A.qname_off = c->qname_off.p; A.qname = c->qname.p; A.upos = c->upos.p; A.score = c->score.p; A.qhash = c->qhash.p;
+        A.ranges = c->d_ranges; A.err = c->d_err;
+        // reads per tile: as many as fit the ring slot on average (256 reads of 150 bases; fewer for longer reads)
+        const double avg_q = (double)(c->n_qual - ARENA_FRONT_PAD) / (double)n + 1, avg_n = (double)c->n_qname / (double)n + 1, avg_c = 4.0 * (double)c->n_cigar / (double)n + 1;
+        int rpt = (int)std::min({(double)AD_T, 0.94 * AD_QCAP / avg_q, 0.94 * AD_NCAP / avg_n, 0.94 * AD_CCAP / avg_c});
+        A.reads_per_tile = std::max(32, rpt & ~31);
+        const uint64_t n_tiles = (n + A.reads_per_tile - 1) / A.reads_per_tile;
+        const unsigned grid = (unsigned)std::min<uint64_t>(n_tiles, (uint64_t)sms);
+        const size_t smem = (size_t)AD_STAGES * AD_STAGE;
+        CUDA_TRY(c, cudaFuncSetAttribute(adapt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        double bytes = (double)n * (2 + 4 + 4 + 16 + 16 + 8 + 4 + 4 + 8) + (double)(c->n_qual - ARENA_FRONT_PAD) + (double)c->n_cigar * 4 + (double)c->n_qname;
         c->begin("adapt", bytes);
-        adapt_kernel<<<grid, 256, 0, c->stream>>>(n, c->flag.p, c->pos.p, c->rg.p, c->d_rg_lib, c->n_rg, c->cigar_off.p, c->cigar.p, c->qual_off.p, c->qual.p,
-                                                  c->qname_off.p, c->qname.p, c->upos.p, c->score.p, c->qhash.p, c->d_ranges, c->d_err);
+        adapt_kernel<<<grid, AD_T, smem, c->stream>>>(A);
         c->end(); LAUNCH_CHECK(c);
     }
     CUDA_TRY(c, cudaMemcpyAsync(&c->h_ranges, c->d_ranges, sizeof(DeviceRanges), cudaMemcpyDeviceToHost, c->stream));

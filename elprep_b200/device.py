@@ -91,6 +91,27 @@ class Context:
         b.l_seq = _vp(batch.lseq)
         self._ck(self.L.elp_append_batch(self.h, C.byref(b)))
 
+    def append_async(self, batch):
+        """queue the upload and return; ``batch`` (page-locked) must stay alive and unchanged until append_wait()"""
+        b = _lib.ElpBatch()
+        b.n = batch.n
+        for k in ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "seq", "qual"):
+            setattr(b, k, _vp(getattr(batch, k)))
+        b.l_seq = _vp(batch.lseq)
+        self._ck(self.L.elp_append_batch_async(self.h, C.byref(b)))
+
+    def append_wait(self):
+        self._ck(self.L.elp_append_wait(self.h))
+
+    def fetch_async(self, out, first=0, n=None):
+        """out = (record_index u32[n], flag u16[n], qual_off u64[n+1] or None, qual u8[]) page-locked; complete after fetch_wait()"""
+        n = self.n - first if n is None else n
+        idx, flag, qoff, qual = out
+        self._ck(self.L.elp_fetch_async(self.h, first, n, _vp(idx), _vp(flag), _vp(qoff), _vp(qual), qual.size if qual is not None else 0))
+
+    def fetch_wait(self):
+        self._ck(self.L.elp_fetch_wait(self.h))
+
     def set_ingest_filter(self, mask=0, min_mapq=0):
         self._ck(self.L.elp_set_ingest_filter(self.h, mask, min_mapq))
 

@@ -107,6 +107,11 @@ int elp_set_known_sites(elp_ctx *ctx, int32_t contig, const int32_t *start_end_p
 
 /* ---- phase 1: (*sam.Sam).AddNodes receiving batches (sam/filter-pipeline.go:108-128) ---- */
 int elp_append_batch(elp_ctx *ctx, const elp_batch *batch);
+/* Asynchronous form for pipelined callers (one context uploads while another computes and downloads): the copies are queued on the
+ * context's ingest stream and the call returns; the caller's buffers -- page-locked, or the copies serialise -- must stay valid and
+ * unchanged until elp_append_wait returns.  Every later phase call of the same context orders itself behind the upload. */
+int elp_append_batch_async(elp_ctx *ctx, const elp_batch *batch);
+int elp_append_wait(elp_ctx *ctx);
 /* The same, straight from decompressed BAM alignment records: what parseBamAlignment reads on the host
  * (sam/bam-files.go:314-400) is parsed on the device instead, so a Go caller hands over the bytes of a BGZF block without
  * building []*sam.Alignment first.  records: n_bytes of consecutive records, each starting with its 4-byte block_size;
@@ -191,6 +196,11 @@ int elp_bqsr_apply(elp_ctx *ctx);
  * flag: FLAG with the 0x400 bits; qual: recalibrated QUAL bytes packed back to back; qual_off[n+1]: offsets into qual. ---- */
 int elp_fetch(elp_ctx *ctx, uint64_t first, uint64_t n, uint64_t *record_index, uint16_t *flag, uint64_t *qual_off, uint8_t *qual, uint64_t qual_capacity);
 uint64_t elp_fetch_qual_bytes(elp_ctx *ctx, uint64_t first, uint64_t n);
+/* Asynchronous form: the device->host copies are queued on the context's download stream (behind everything the phases computed) and the
+ * call returns; the buffers are complete when elp_fetch_wait returns.  record_index32: the permutation as 32-bit indices (a context
+ * holds fewer than 2^32 reads). */
+int elp_fetch_async(elp_ctx *ctx, uint64_t first, uint64_t n, uint32_t *record_index32, uint16_t *flag, uint64_t *qual_off, uint8_t *qual, uint64_t qual_capacity);
+int elp_fetch_wait(elp_ctx *ctx);
 /* per-read temps of adaptAlignment (filters/mark-duplicates.go:153-156), arrival order; for parity tests */
 /* The same as BAM alignment records (only if every read came in through elp_append_bam): output records [first, first+n) are
  * the stored records with FLAG and -- once elp_bqsr_apply has run -- QUAL replaced; names, CIGAR and optional fields are the
