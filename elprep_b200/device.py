@@ -192,6 +192,23 @@ class Context:
         t = np.ascontiguousarray(t, dtype=np.int64)
         self._ck(self.L.elp_bqsr_tables_put(self.h, _vp(t), t.size))
 
+    def tables_clear(self):
+        self._ck(self.L.elp_bqsr_tables_clear(self.h))
+
+    def write_elrecal(self, path):
+        """gob of filters.BaseRecalibratorTables, what `--bqsr-tables-only` leaves for the merge step"""
+        self._ck(self.L.elp_bqsr_tables_write_elrecal(self.h, path.encode()))
+
+    def add_elrecal(self, path):
+        """LoadAndCombineBQSRTables for one file: its counters are added to the context's tables"""
+        self._ck(self.L.elp_bqsr_tables_add_elrecal(self.h, path.encode()))
+
+    def optical_write_gob(self, path):
+        self._ck(self.L.elp_optical_write_gob(self.h, path.encode()))
+
+    def optical_add_gob(self, path):
+        self._ck(self.L.elp_optical_add_gob(self.h, path.encode()))
+
     def tables_device(self):
         p, n = C.c_void_p(), C.c_uint64()
         self._ck(self.L.elp_bqsr_tables_device(self.h, C.byref(p), C.byref(n)))

@@ -240,6 +240,10 @@ class BaseRecalibratorTables:
         """bqsrTable.merge (filters/bqsr.go:210-223) / LoadAndCombineBQSRTables (print-bqsr.go:310-329): add another table."""
         self.reads.ctx.tables_put(self.dense() + np.asarray(dense, dtype=np.int64))
 
+    def PrintBQSRTablesToIntermediateFile(self, name):
+        """filters/print-bqsr.go:300-308: the `--bqsr-tables-only` worker's output (cmd/filter.go:454, 955-983), gob of the three tables"""
+        self.reads.ctx.write_elrecal(name)
+
     def FinalizeBQSRTables(self):
         """filters/bqsr.go:677-694"""
         self.reads.ctx.bqsr_finalize(None)
@@ -261,6 +265,32 @@ class BaseRecalibratorTables:
                 self.FinalizeBQSRTables()
             return _DeviceOp("apply")
         return flt
+
+
+def LoadAndCombineBQSRTables(reads, bqsrPath):
+    """filters.LoadAndCombineBQSRTables (filters/print-bqsr.go:310-329): sums every .elrecal file of a directory (or the one file) into the
+    tables of ``reads``' context -- the input of the `--bqsr-apply` worker (cmd/filter.go:455, 985-997), which then runs
+    FinalizeBQSRTables + PrintBQSRTables(recal file) and the ApplyBQSR filter (runBestPracticesPipelineWithBQSRApplyOnly, cmd/filter.go:213-234)."""
+    import os
+    files = sorted(os.path.join(bqsrPath, f) for f in os.listdir(bqsrPath)) if os.path.isdir(bqsrPath) else [bqsrPath]
+    reads.ctx.tables_clear()
+    for f in files:
+        reads.ctx.add_elrecal(f)
+    return BaseRecalibratorTables(reads)
+
+
+def PrintDuplicatesMetricsToIntermediateFile(reads, name):
+    """filters/mark-optical-duplicates.go:701-709: the worker's counters as gob of map[string]*DuplicatesCtr"""
+    reads.ctx.optical_write_gob(name)
+
+
+def LoadAndCombineDuplicateMetrics(reads, metricsPath):
+    """filters/mark-optical-duplicates.go:711-731: adds the counters of every file to the context's metrics (derived values are recomputed on read-out)"""
+    import os
+    files = sorted(os.path.join(metricsPath, f) for f in os.listdir(metricsPath)) if os.path.isdir(metricsPath) else [metricsPath]
+    for f in files:
+        reads.ctx.optical_add_gob(f)
+    return dict(zip(reads.ctx.optical_libraries(), reads.ctx.optical_metrics()))
 
 
 def _lib_const(name):

@@ -181,6 +181,20 @@ int elp_bqsr_tables_get(elp_ctx *ctx, int64_t *dense, uint64_t n);
 int elp_bqsr_tables_put(elp_ctx *ctx, const int64_t *dense, uint64_t n);
 int elp_bqsr_tables_device(elp_ctx *ctx, void **device_ptr, uint64_t *n);
 
+/* The same exchange as Go encoding/gob files, for a GPU worker inside an `elprep sfm` run (cmd/filter.go:454-455, 955-997):
+ *   --bqsr-tables-only f :  elp_bqsr_gather, then elp_bqsr_tables_write_elrecal(f)     (PrintBQSRTablesToIntermediateFile, filters/print-bqsr.go:300-308)
+ *   --bqsr-apply dir     :  elp_bqsr_tables_clear, elp_bqsr_tables_add_elrecal(each file of dir) (LoadAndCombineBQSRTables, :310-329),
+ *                           then elp_bqsr_finalize(recal file) and elp_bqsr_apply       (runBestPracticesPipelineWithBQSRApplyOnly, cmd/filter.go:213-234)
+ * The stream is gob of filters.BaseRecalibratorTables{QualityScores, Cycles, Contexts map[bqsrTableKey{Qual,Covariate,ReadGroup}]*bqsrEntry};
+ * written per the encoding/gob specification, not checked against a Go binary (none in this image). */
+int elp_bqsr_tables_clear(elp_ctx *ctx);
+int elp_bqsr_tables_write_elrecal(elp_ctx *ctx, const char *path);
+int elp_bqsr_tables_add_elrecal(elp_ctx *ctx, const char *path);
+/* duplication metrics of a worker as gob of map[string]*DuplicatesCtr (the seven exported counters;
+ * PrintDuplicatesMetricsToIntermediateFile / LoadAndCombineDuplicateMetrics, filters/mark-optical-duplicates.go:701-731) */
+int elp_optical_write_gob(elp_ctx *ctx, const char *path);
+int elp_optical_add_gob(elp_ctx *ctx, const char *path);
+
 /* ---- phase 4: FinalizeBQSRTables + PrintBQSRTables (filters/bqsr.go:677-694, filters/print-bqsr.go:269-298).
  * report_path may be NULL (no report). Also builds the apply look-up table. ---- */
 int elp_bqsr_finalize(elp_ctx *ctx, const char *report_path);
