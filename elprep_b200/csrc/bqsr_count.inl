@@ -270,7 +270,12 @@ __global__ void __launch_bounds__(CNT_WARPS * 32, 2) bqsr_count_kernel(CountArgs
                 lanes::LaneS1<S> s1;
                 lanes::lane_stage1<S, INDEL>(lw, lr, c, A.sh, A.lut_lo, A.lut_hi, RT, s1);
                 // low-quality tails: first / last base of the READ with QUAL > 2, over the lanes of the read
-                const int leftPos = __reduce_min_sync(gmask, s1.lf), rightPos = __reduce_max_sync(gmask, s1.ll);
+                // (a segmented REDUX compiles to a loop over the distinct member masks: one vote and two shuffles instead.  Kept-read coordinates
+                // grow with the lane for forward reads and fall for reverse reads, so the extreme positions sit in the first / last lane that has any)
+                const unsigned gb = __ballot_sync(FULL_MASK, s1.ll >= 0) & gmask;
+                const int lo_lane = gb ? __ffs((int)gb) - 1 : (int)lane, hi_lane = gb ? 31 - __clz((int)gb) : (int)lane;
+                const int lf_x = __shfl_sync(FULL_MASK, s1.lf, rev ? hi_lane : lo_lane), ll_x = __shfl_sync(FULL_MASK, s1.ll, rev ? lo_lane : hi_lane);
+                const int leftPos = gb ? lf_x : 0x7fffffff, rightPos = gb ? ll_x : -1;
                 lanes::LaneS2<S> s2;
                 lanes::lane_stage2<S>(s1, lr, c, leftPos, rightPos, RT, s2);
                 uint32_t ein = __shfl_up_sync(FULL_MASK, s2.epack, 1);     // the base before this lane's first one belongs to the lane below

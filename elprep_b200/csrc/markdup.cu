@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256) join_keys_kernel(uint64_t n, const uint16
     if (i >= n) return;
     const uint16_t f = flag[i];
     const bool in = (f & (F_UNMAPPED | F_SECONDARY | F_SUPPLEMENTARY)) == 0 && (f & (F_MULTIPLE | F_NEXTUNMAPPED)) == F_MULTIPLE;
-    keys[i] = in ? (qhash[i] & ((1ull << 39) - 1)) : (1ull << 39);
+    keys[i] = in ? (qhash[i] & 0x7fffffffull) : (1ull << 31);      // 31 hash bits + the "not a true pair" bit = 32 key bits = 4 passes (equal-hash runs are verified on bytes)
     vals[i] = (uint32_t)i;
     mate[i] = NONE;
 }
@@ -481,7 +481,7 @@ int phase_markdup(elp_ctx* c, bool optical) {
         join_keys_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->flag.p, c->qhash.p, c->keys_a.p, c->vals_a.p, c->mate.p);
         c->end(); LAUNCH_CHECK(c);
         bool in_b = false;
-        rc = radix_sort_u64(c, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, 40, &in_b, "u64");
+        rc = radix_sort_u64(c, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, 32, &in_b, "u64");   // 31 hash bits + 1: runs of equal hash are verified on bytes anyway
         if (rc) return rc;
         const uint64_t m = R.n_true_pairs;
         c->begin("join", (double)m * 12);
