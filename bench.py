@@ -9,9 +9,9 @@ Timing: CUDA events on the library's own stream (elp_timer_start/stop), barrier 
 Each step re-ingests ~270 B/read (>> the 126 MB L2), so no kernel ever sees a warm L2 from the previous step.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl reference]
-N>1 is launched by torchrun (one rank per GPU): every rank owns one contig group of an hg38-shaped genome (sfm-style
-partition, cmd/sfm.go; mates never cross groups in this synthetic input), the only collective is one NCCL allreduce
-of the integer BQSR tables.  --impl reference times the CPU restatement of the reference algorithm (oracle/, the Go
+N>1 is launched by torchrun (one rank per GPU): ONE hg38-shaped genome is partitioned over the ranks by contig group (sfm-style,
+cmd/sfm.go); 1 % of the pairs span two groups.  All cross-GPU traffic of the hot path is NCCL inside the library (C ABI): the spread-pair
+exchange of elp_sort_markdup (grouped ncclSend/ncclRecv of 128-byte mate records) and one ncclAllReduce of the integer BQSR tables.  --impl reference times the CPU restatement of the reference algorithm (oracle/, the Go
 toolchain being absent) on the host cores, on a bounded sample of the same workload.
 """
 import argparse
@@ -105,7 +105,7 @@ def cpu_pipeline(w, n_reads, threads):
     t1 = time.perf_counter()
     srt = synth.take(b, perm, threads=threads)            # (*sam.Sam) sorts pointers; materialising the order is not part of the reference's work
     t2 = time.perf_counter()
-    ref = oracle.Reference(w.header, w.contig_bases, w.sites)
+    ref = oracle.Reference(w.header, [b if b is not None else np.zeros(0, np.uint8) for b in w.contig_bases], w.sites)
     t3 = time.perf_counter()
     tb = oracle.bqsr_gather(srt, w.header, ref, n_threads=threads)
     oracle.bqsr_finalize(tb)
@@ -162,7 +162,8 @@ def main():
     groups = contig_groups(all_contigs, world)
     contigs = groups[rank]
     threads = min(os.cpu_count() or 1, 64)
-    workload_name = f"hg38/{GENOME_SCALE / world:g}-shaped genome split into {world} contig group(s), {args.reads} synthetic 150-bp paired reads per GPU, sort+markdup+BQSR(gather,finalize,apply)"
+    workload_name = (f"one hg38/{GENOME_SCALE / world:g}-shaped genome partitioned into {world} contig group(s) (1 % of the pairs span two groups), "
+                     f"{args.reads} synthetic 150-bp paired reads per GPU, sort+markdup+BQSR(gather,finalize,apply)")
 
     if args.impl == "reference":
         if rank != 0:
@@ -192,18 +193,38 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t0 = time.time()
-    w = synth.make_workload(args.reads // 2, contigs, seed=20260924 + rank, threads=max(4, threads // max(1, world)))
-    log(f"[rank {rank}] generated {w.batch.n} reads over {len(contigs)} contigs in {time.time() - t0:.1f}s")
-    hb = pinned(w.batch)
+    owner = None
+    if world == 1:
+        w = synth.make_workload(args.reads // 2, contigs, seed=20260924, threads=max(4, threads))
+        header, batch, my_contigs = w.header, w.batch, list(range(len(contigs)))
+    else:
+        # ONE genome partitioned over the ranks by contig group (sfm-style): each rank generates the pairs whose fragment starts in its group; the
+        # mates of its cross-contig pairs (1 % of the pairs) land on any contig, so pairs span ranks.  The split step hands every read to the
+        # rank that owns its contig (host-side setup, untimed) -- after it a rank holds exactly the reads `elprep split` would have put in its file.
+        from elprep_b200 import multi
+        header = synth.make_header(all_contigs)
+        owner = multi.owner_table(header, groups)
+        my_contigs = [i for i in range(len(all_contigs)) if owner[i] == rank]
+        home = np.array([1 if owner[i] == rank else 0 for i in range(len(all_contigs))], np.uint8)
+        w = synth.make_workload(args.reads // 2, all_contigs, seed=20260924 + rank, home=home, pair_id_base=rank * 10**10, genome_seed=20260924,
+                                reference_for=my_contigs, threads=max(4, threads // max(1, world)))
+        batch = multi.redistribute(w.batch, owner, rank, world, multi.torch_gather_objects())
+        w.batch = batch
+    log(f"[rank {rank}] {batch.n} reads on {len(my_contigs)} of {len(all_contigs)} contigs, generated in {time.time() - t0:.1f}s")
+    hb = pinned(batch)
     n_reads = hb.n
     h2d = sum(getattr(hb, f).nbytes for f in hb.FIELDS)
 
     def make_ctx():
-        cx = device.Context(w.header, device=local, profile=True)
-        for ci in range(len(contigs)):
+        cx = device.Context(header, device=local, profile=True)
+        for ci in my_contigs:
             cx.set_reference(ci, w.contig_bases[ci])
             cx.set_known_sites(ci, w.sites[ci], already_flat=True)
         cx.reserve(n_reads, int(hb.qual.size), int(hb.cigar.size), int(hb.qname.size))
+        if world > 1:     # NCCL behind the C ABI: communicator per context, contig -> rank table
+            uid = [device.Context.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            cx.comm_init(uid[0], rank, world); cx.comm_set_partition(owner)
         return cx
     ctx = make_ctx()
     # pinned output buffers for the fetch: 32-bit record indices, FLAG, QUAL offsets, QUAL bytes
@@ -211,13 +232,6 @@ def main():
     out_np = (out[0].numpy().view(np.uint32), out[1].numpy().view(np.uint16), out[2].numpy().view(np.uint64), out[3].numpy())
     d2h = sum(a.nbytes for a in out_np)
 
-    def alias_tables(cx):
-        ptr, nvals = cx.tables_device()
-
-        class _Alias:
-            __cuda_array_interface__ = {"shape": (nvals,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-        return torch.as_tensor(_Alias(), device=f"cuda:{local}")
-    tables_t = {id(ctx): alias_tables(ctx)} if world > 1 else {}
 
     def barrier(cx):
         cx.synchronize(); torch.cuda.synchronize()
@@ -230,9 +244,9 @@ def main():
         cx.bqsr_gather()
         t_coll = 0.0
         if dist:
-            cx.tables_device()
+            cx.synchronize()
             t0 = time.perf_counter()
-            dist.all_reduce(tables_t[id(cx)]); torch.cuda.synchronize()
+            cx.tables_allreduce(); cx.synchronize()           # ncclAllReduce(sum, int64) inside the library, on the context's stream
             t_coll = 1e3 * (time.perf_counter() - t0)
         cx.bqsr_finalize(None)
         cx.bqsr_apply()
@@ -269,8 +283,6 @@ def main():
     # ---- e2e: the same K steps through the public API with host buffers, software-pipelined over two contexts: while context A's
     # batch uploads, context B (previous step) runs its device phases and downloads.  Every step still moves its full input and output.
     ctx2 = make_ctx()
-    if world > 1:
-        tables_t[id(ctx2)] = alias_tables(ctx2)
     cs = (ctx, ctx2)
 
     def e2e_run(k_steps):
@@ -353,7 +365,7 @@ def main():
         verified = verify_against_oracle(ctx, w, out_np, n_reads, threads)
     line = {"metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
-            "config": {"workload": workload_name, "cpu_arm": f"CPU arm runs a sample: the first {args.cpu_sample} reads per step", "reads_per_gpu": n_reads, "parallelism": f"contig-group x{world}", "flush": "inputs >> L2 (re-ingested every step)"},
+            "config": {"workload": workload_name, "cpu_arm": f"CPU arm runs a sample: the first {args.cpu_sample} reads per step", "reads_per_gpu": n_reads, "parallelism": f"contig-group x{world}; NCCL inside the C ABI: spread-pair exchange (ncclSend/Recv) in elp_sort_markdup + one ncclAllReduce of the BQSR tables", "flush": "inputs >> L2 (re-ingested every step)"},
             "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
                     "how": "K steps through elp_append_batch_async / phases / elp_fetch_async with pinned host buffers, software-pipelined over two contexts (upload of step s overlaps phases + download of step s-1)",
                     "unpipelined_ms_per_step": float(np.mean(in_ms) + np.mean(dev_ms) + np.mean(out_ms))},

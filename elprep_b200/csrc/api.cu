@@ -185,6 +185,9 @@ void elp_destroy(elp_ctx* c) {
     for (auto& pe : c->pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
     for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->timer_a) { cudaEventDestroy(c->timer_a); cudaEventDestroy(c->timer_b); }
+    elp_comm_destroy(c);
+    if (c->d_owner) cudaFree(c->d_owner);
+    c->sp_sendbuf.release(); c->sp_recvbuf.release(); c->sp_sent_idx.release();
     if (c->copy_in) { cudaStreamDestroy(c->copy_in); cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_staged); }
     if (c->copy_out) { cudaStreamDestroy(c->copy_out); cudaEventDestroy(c->ev_out); }
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -271,6 +274,17 @@ static uint64_t sum_lengths(const int32_t* l, uint64_t n, uint64_t* seq_bytes) {
     *seq_bytes = y; return x;
 }
 
+// Large host<->device copies go out in pieces: a copy engine serves its queue in order, so one 4 GB cudaMemcpyAsync would hold up every
+// small copy of the OTHER contexts of a pipelined caller (the few-byte read-backs and table uploads inside their phases) until it is done.
+static cudaError_t copy_chunked(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
+    const size_t CH = 32u << 20;
+    for (size_t o = 0; o < bytes; o += CH) {
+        cudaError_t e = cudaMemcpyAsync((char*)dst + o, (const char*)src + o, std::min(CH, bytes - o), kind, s);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 static int append_impl(elp_ctx* c, const elp_batch* b, bool wait) {
     cudaSetDevice(c->device);
     std::lock_guard<std::mutex> lk(c->append_mu);
@@ -296,18 +310,18 @@ static int append_impl(elp_ctx* c, const elp_batch* b, bool wait) {
     CUDA_TRY(c, cudaEventRecord(c->ev_staged, s)); CUDA_TRY(c, cudaStreamWaitEvent(ci, c->ev_staged, 0));
     TRY(grow(c, c->off_stage, 2 * (bn + 2), 0)); TRY(grow(c, c->lseq_stage, bn + 2, 0)); TRY(grow(c, c->scan_tmp, 2 * bn + 8, 0));
     const cudaMemcpyKind H2D = cudaMemcpyHostToDevice;
-    CUDA_TRY(c, cudaMemcpyAsync(c->refid.p + n0, b->refid, bn * 4, H2D, ci)); CUDA_TRY(c, cudaMemcpyAsync(c->pos.p + n0, b->pos, bn * 4, H2D, ci));
-    CUDA_TRY(c, cudaMemcpyAsync(c->nref.p + n0, b->nref, bn * 4, H2D, ci)); CUDA_TRY(c, cudaMemcpyAsync(c->pnext.p + n0, b->pnext, bn * 4, H2D, ci));
-    CUDA_TRY(c, cudaMemcpyAsync(c->tlen.p + n0, b->tlen, bn * 4, H2D, ci)); CUDA_TRY(c, cudaMemcpyAsync(c->rg.p + n0, b->rg, bn * 4, H2D, ci));
-    CUDA_TRY(c, cudaMemcpyAsync(c->flag.p + n0, b->flag, bn * 2, H2D, ci)); CUDA_TRY(c, cudaMemcpyAsync(c->mapq.p + n0, b->mapq, bn, H2D, ci));
+    CUDA_TRY(c, copy_chunked(c->refid.p + n0, b->refid, bn * 4, H2D, ci)); CUDA_TRY(c, copy_chunked(c->pos.p + n0, b->pos, bn * 4, H2D, ci));
+    CUDA_TRY(c, copy_chunked(c->nref.p + n0, b->nref, bn * 4, H2D, ci)); CUDA_TRY(c, copy_chunked(c->pnext.p + n0, b->pnext, bn * 4, H2D, ci));
+    CUDA_TRY(c, copy_chunked(c->tlen.p + n0, b->tlen, bn * 4, H2D, ci)); CUDA_TRY(c, copy_chunked(c->rg.p + n0, b->rg, bn * 4, H2D, ci));
+    CUDA_TRY(c, copy_chunked(c->flag.p + n0, b->flag, bn * 2, H2D, ci)); CUDA_TRY(c, copy_chunked(c->mapq.p + n0, b->mapq, bn, H2D, ci));
     uint64_t* st_q = c->off_stage.p; uint64_t* st_c = c->off_stage.p + (bn + 2);
-    CUDA_TRY(c, cudaMemcpyAsync(st_q, b->qname_off, (bn + 1) * 8, H2D, ci));
-    CUDA_TRY(c, cudaMemcpyAsync(st_c, b->cigar_off, (bn + 1) * 8, H2D, ci));
-    CUDA_TRY(c, cudaMemcpyAsync(c->lseq_stage.p, b->l_seq, bn * 4, H2D, ci));
-    if (bq) CUDA_TRY(c, cudaMemcpyAsync(c->qname.p + c->n_qname, b->qname + b->qname_off[0], bq, H2D, ci));
-    if (bc) CUDA_TRY(c, cudaMemcpyAsync(c->cigar.p + c->n_cigar, b->cigar + b->cigar_off[0], bc * 4, H2D, ci));
-    if (bseq) CUDA_TRY(c, cudaMemcpyAsync(c->seq.p + c->n_seq, b->seq, bseq, H2D, ci));
-    if (bbases) CUDA_TRY(c, cudaMemcpyAsync(c->qual.p + c->n_qual, b->qual, bbases, H2D, ci));
+    CUDA_TRY(c, copy_chunked(st_q, b->qname_off, (bn + 1) * 8, H2D, ci));
+    CUDA_TRY(c, copy_chunked(st_c, b->cigar_off, (bn + 1) * 8, H2D, ci));
+    CUDA_TRY(c, copy_chunked(c->lseq_stage.p, b->l_seq, bn * 4, H2D, ci));
+    if (bq) CUDA_TRY(c, copy_chunked(c->qname.p + c->n_qname, b->qname + b->qname_off[0], bq, H2D, ci));
+    if (bc) CUDA_TRY(c, copy_chunked(c->cigar.p + c->n_cigar, b->cigar + b->cigar_off[0], bc * 4, H2D, ci));
+    if (bseq) CUDA_TRY(c, copy_chunked(c->seq.p + c->n_seq, b->seq, bseq, H2D, ci));
+    if (bbases) CUDA_TRY(c, copy_chunked(c->qual.p + c->n_qual, b->qual, bbases, H2D, ci));
     CUDA_TRY(c, cudaEventRecord(c->ev_in, ci));
     CUDA_TRY(c, cudaStreamWaitEvent(s, c->ev_in, 0));
     // offsets: batch-relative -> arena-global
@@ -423,11 +437,11 @@ static int fetch_impl(elp_ctx* c, uint64_t first, uint64_t n, uint64_t* record_i
     LAUNCH_CHECK(c);
     // everything the compute stream produced so far (apply, the two small kernels above) -> the download stream
     CUDA_TRY(c, cudaEventRecord(c->ev_out, s)); CUDA_TRY(c, cudaStreamWaitEvent(co, c->ev_out, 0));
-    if (qual) CUDA_TRY(c, cudaMemcpyAsync(qual, c->qual_out.p + v[0], v[1] - v[0], cudaMemcpyDeviceToHost, co));
-    if (record_index) CUDA_TRY(c, cudaMemcpyAsync(record_index, c->off_stage.p, n * 8, cudaMemcpyDeviceToHost, co));
-    if (record_index32) CUDA_TRY(c, cudaMemcpyAsync(record_index32, c->perm.p + first, n * 4, cudaMemcpyDeviceToHost, co));
-    if (flag) CUDA_TRY(c, cudaMemcpyAsync(flag, c->s_flag.p + first, n * 2, cudaMemcpyDeviceToHost, co));
-    if (qual_off) CUDA_TRY(c, cudaMemcpyAsync(qual_off, c->off_stage.p + (n + 2), (n + 1) * 8, cudaMemcpyDeviceToHost, co));
+    if (qual) CUDA_TRY(c, copy_chunked(qual, c->qual_out.p + v[0], v[1] - v[0], cudaMemcpyDeviceToHost, co));
+    if (record_index) CUDA_TRY(c, copy_chunked(record_index, c->off_stage.p, n * 8, cudaMemcpyDeviceToHost, co));
+    if (record_index32) CUDA_TRY(c, copy_chunked(record_index32, c->perm.p + first, n * 4, cudaMemcpyDeviceToHost, co));
+    if (flag) CUDA_TRY(c, copy_chunked(flag, c->s_flag.p + first, n * 2, cudaMemcpyDeviceToHost, co));
+    if (qual_off) CUDA_TRY(c, copy_chunked(qual_off, c->off_stage.p + (n + 2), (n + 1) * 8, cudaMemcpyDeviceToHost, co));
     if (wait) CUDA_TRY(c, cudaStreamSynchronize(co));
     return ELP_OK;
 }

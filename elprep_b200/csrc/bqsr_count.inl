@@ -16,7 +16,14 @@
 // [H][S]M[S][H] or that plus one insertion/deletion; everything else goes to the old, general kernels through a list).
 // QUAL, SEQ and reference windows are staged through shared memory with cp.async, three passes deep.
 
-constexpr int CNT_WARPS = 8, CNT_STAGES = 3, CNT_RECRING = 6, SEG_PASSES = 255, MAX_CLS = 64;
+#ifndef CNT_MINB
+#define CNT_MINB 2
+#endif
+#ifndef CNT_STAGES_N
+#define CNT_STAGES_N 3
+#endif
+// software pipeline of a warp: records are fetched CNT_D2 iterations, windows CNT_D2 - CNT_D1 iterations ahead of their use; CNT_WN copy groups stay in flight
+constexpr int CNT_WARPS = 8, CNT_STAGES = CNT_STAGES_N, CNT_WN = CNT_STAGES - 1, CNT_D1 = CNT_WN + 1, CNT_D2 = 2 * CNT_WN + 1, CNT_RECRING = CNT_D2 + 1, SEG_PASSES = 255, MAX_CLS = 64;
 constexpr uint32_t KEY_NONE = 0xffffffffu;
 
 struct Prep2Args {
@@ -159,7 +166,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.
 __device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) { asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
 
 template <int S, bool INDEL>
-__global__ void __launch_bounds__(CNT_WARPS * 32, 2) bqsr_count_kernel(CountArgs A) {
+__global__ void __launch_bounds__(CNT_WARPS * 32, CNT_MINB) bqsr_count_kernel(CountArgs A) {
     constexpr int NCH = INDEL ? 9 : 7;                                  // 16-byte chunks per lane and pass: QUAL 3, SEQ 2, REF 2 (+2)
     constexpr int STAGE_BYTES = NCH * 512;                              // per warp
     const uint32_t REC_BYTES = A.rec_bytes, WARP_BYTES = CNT_STAGES * STAGE_BYTES + CNT_RECRING * REC_BYTES;
@@ -194,14 +201,14 @@ __global__ void __launch_bounds__(CNT_WARPS * 32, 2) bqsr_count_kernel(CountArgs
 #pragma unroll
         for (int i = 0; i < 8 * S; i++) cx[i] = 0;
 
-        for (int it = 0; it < n_pass + 5; it++) {
-            // ---- (a) records of pass `it` -> ring slot it % 6 ----
+        for (int it = 0; it < n_pass + CNT_D2; it++) {
+            // ---- (a) records of pass `it` -> ring slot it % CNT_RECRING ----
             if (it < n_pass) {
                 const uint32_t nrec_here = min((uint32_t)rpw, n_rec - (uint32_t)it * (uint32_t)rpw);
                 for (uint32_t x = lane; x < 2 * nrec_here; x += 32) cp_async16(rbase + (uint32_t)(it % CNT_RECRING) * REC_BYTES + x * 16u, A.recs + 2 * ((uint64_t)rec_first + (uint64_t)it * rpw) + x);
             }
-            // ---- (b) QUAL / SEQ / reference windows of pass it - 3 -> stage (it - 3) % 3 ----
-            const int pd = it - 3;
+            // ---- (b) QUAL / SEQ / reference windows of pass it - CNT_D1 -> its stage ----
+            const int pd = it - CNT_D1;
             if (pd >= 0 && pd < n_pass && lane_used && (uint32_t)(pd * rpw + r) < n_rec) {
                 const uint32_t ra = rbase + (uint32_t)(pd % CNT_RECRING) * REC_BYTES + (uint32_t)r * 32u;
                 const uint4 r0 = lds128(ra), r1 = lds128(ra + 16);
@@ -229,10 +236,10 @@ __global__ void __launch_bounds__(CNT_WARPS * 32, 2) bqsr_count_kernel(CountArgs
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 2;" ::: "memory");
+            asm volatile("cp.async.wait_group %0;" ::"n"(CNT_WN) : "memory");
             __syncwarp();
-            // ---- (c) compute pass it - 5 ----
-            const int pc = it - 5;
+            // ---- (c) compute pass it - CNT_D2 ----
+            const int pc = it - CNT_D2;
             if (pc >= 0) {
                 const bool have = lane_used && (uint32_t)(pc * rpw + r) < n_rec;
                 const uint32_t ra = rbase + (uint32_t)(pc % CNT_RECRING) * REC_BYTES + (uint32_t)r * 32u;

@@ -966,7 +966,7 @@ int phase_bqsr_gather(elp_ctx* c) {
             K.qual = c->qual.p; K.seq = c->seq.p; K.refhot = c->d_refhot_ptrs; K.recs = c->bq_recs.p; K.tables = A.tables; K.geom = c->geom;
             K.lpr = lpr; K.rpw = rpw; K.rec_bytes = 32u * (uint32_t)rpw; K.sh = F.sh; K.lut_lo = F.lut_lo; K.lut_hi = F.lut_hi;
             for (int s = 0; s < 4; s++) K.slot_q[s] = F.slot_q[s];
-            const unsigned grid = (unsigned)sms * 2;
+            const unsigned grid = (unsigned)sms * CNT_MINB;
             for (int v = 0; v < 2; v++) {
                 K.segs = v ? segs1 : segs0; K.n_seg = d_nseg + v; K.seg_next = d_next + v;
                 c->begin(v ? "bqsr_g_count_indel" : "bqsr_g_count", 0);     // bytes are set below, once the list sizes are known

@@ -156,6 +156,15 @@ struct elp_ctx {
     std::vector<DupCounters> opt;             // [n_lib + 1], slot 0 = "Unknown Library"
     bool opt_valid = false;
 
+    // ---- several GPUs (comm.cu) ----
+    void* comm = nullptr;                     // ncclComm_t
+    int rank = 0, world = 1;
+    int32_t* d_owner = nullptr;               // [n_contigs] rank owning each contig
+    uint64_t n_ghost = 0, sp_sent_total = 0;  // visiting mates appended behind the local reads during duplicate marking; records this rank sent
+    std::vector<uint32_t> sp_send, sp_recv;   // records to / from every rank
+    DBuf<uint4> sp_sendbuf, sp_recvbuf; DBuf<uint32_t> sp_sent_idx;
+    bool any_rank_entering = true;
+
     // ---- measurement ----
     uint64_t launches = 0;
     std::map<std::string, KernelStat> stats;
@@ -222,4 +231,8 @@ int build_apply_lut(elp_ctx* c, int Lc);   // bqsr_finalize.cu
 int upload_side_inputs(elp_ctx* c);
 int pack_reference(elp_ctx* c, int contig);
 int check_device_errors(elp_ctx* c);
+int comm_allreduce_ranges(elp_ctx* c);   // comm.cu
+int spread_exchange_begin(elp_ctx* c);
+int spread_exchange_end(elp_ctx* c);
+int exclusive_scan_u64_from_u32(elp_ctx* c, const uint32_t* in, uint64_t* out, uint64_t n, uint64_t base);   // out[n+1], out[0] = base
 int qual_presence_update(elp_ctx* c, uint64_t first_byte, uint64_t n_bytes);   // api.cu: called by both ingest paths

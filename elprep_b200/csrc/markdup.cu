@@ -410,6 +410,7 @@ int check_device_errors(elp_ctx* c) {
     if (e & DERR_BAM_RG) return c->fail(E_BAM, "BAM record with an RG:Z value that is not an @RG ID of the header");
     if (e & DERR_BAM) return c->fail(E_BAM, "malformed BAM alignment record (field lengths and block_size do not add up)");
     if (e & DERR_READLEN_LIMIT) return c->fail(E_LIMIT, "BQSR: read longer than the device kernel supports");
+    if (e & DERR_SPREAD_NAME) return c->fail(E_LIMIT, "cross-group pair exchange: QNAME longer than 92 bytes");
     return c->fail(E_CUDA, "unknown device error word 0x%x", e);
 }
 
@@ -448,76 +449,94 @@ int phase_adapt(elp_ctx* c) {
     return E_OK;
 }
 
+// pairs (classifyPair) over the local reads plus the ghost reads spread_exchange_begin appended (comm.cu); ghosts are true pairs by construction
+static int mark_pairs(elp_ctx* c, bool optical, uint64_t nt, uint64_t n_true_pairs, int bU, int bR, int bL) {
+    const DeviceRanges& R = c->h_ranges;
+    int rc;
+    if (n_true_pairs < 2) return optical ? phase_optical(c, 0, nullptr, nullptr, 0) : E_OK;
+    CUDA_TRY(c, c->mate.reserve(nt + 4, c->stream));
+    c->begin("join_keys", (double)nt * (2 + 8 + 8 + 4 + 4));
+    join_keys_kernel<<<nblk(nt, 256), 256, 0, c->stream>>>(nt, c->flag.p, c->qhash.p, c->keys_a.p, c->vals_a.p, c->mate.p);
+    c->end(); LAUNCH_CHECK(c);
+    bool in_b = false;
+    rc = radix_sort_u64(c, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, nt, 32, &in_b, "u64");   // 31 hash bits + 1: runs of equal hash are verified on bytes anyway
+    if (rc) return rc;
+    const uint64_t m = n_true_pairs;
+    c->begin("join", (double)m * 12);
+    join_kernel<<<nblk(m, 256), 256, 0, c->stream>>>(m, in_b ? c->keys_b.p : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, c->rg.p, c->d_rg_lib, c->n_rg, c->qname_off.p, c->qname.p, c->mate.p);
+    c->end(); LAUNCH_CHECK(c);
+    // deterministic pair list, ordered by the arrival of the later mate
+    CUDA_TRY(c, c->scan_tmp.reserve(nt + 4, c->stream));
+    uint64_t* slot = c->keys_b.p;   // nt+1 u64, free at this point
+    c->begin("pair_flag", (double)nt * 8);
+    pair_flag_kernel<<<nblk(nt, 256), 256, 0, c->stream>>>(nt, c->mate.p, c->scan_tmp.p);
+    c->end(); LAUNCH_CHECK(c);
+    rc = exclusive_scan_u32_to_u64(c, c->scan_tmp.p, slot, nt);
+    if (rc) return rc;
+    uint64_t npairs = 0;
+    CUDA_TRY(c, cudaMemcpyAsync(&npairs, slot + nt, 8, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (npairs >= (optical ? 1u : 2u)) {
+        CUDA_TRY(c, c->pair_a.reserve(npairs + 4, c->stream)); CUDA_TRY(c, c->pair_b.reserve(npairs + 4, c->stream));
+        PairLayout L{}; L.bS = bits_for((uint64_t)R.score_max * 2); L.bU = bU; L.bR = bR; L.bL = bL; L.upos_min = R.upos_min; L.score_max = R.score_max * 2;
+        L.key_bits = L.bS + 2 * L.bU + 2 + 2 * L.bR + L.bL;
+        if (L.key_bits > 128) return c->fail(E_LIMIT, "pair signature needs %d bits (>128)", L.key_bits);
+        // 128-bit keys live in keys_a as (lo,hi) pairs; slot[] occupies keys_b, so sort into a separate buffer
+        CUDA_TRY(c, c->bytes_tmp.reserve((size_t)npairs * 16 + 64, c->stream));
+        uint64_t* kb2 = reinterpret_cast<uint64_t*>(c->bytes_tmp.p);
+        c->begin("pair_keys", (double)nt * 12 + (double)npairs * (2 * 18 + 16 + 12));
+        pair_keys_kernel<<<nblk(nt, 256), 256, 0, c->stream>>>(nt, c->mate.p, slot, c->flag.p, c->refid.p, c->rg.p, c->d_rg_lib, c->n_rg, c->upos.p, c->score.p, L,
+                                                              c->keys_a.p, c->vals_a.p, c->pair_a.p, c->pair_b.p);
+        c->end(); LAUNCH_CHECK(c);
+        rc = radix_sort_u128(c, c->keys_a.p, kb2, c->vals_a.p, c->vals_b.p, npairs, L.key_bits, &in_b, "u128");
+        if (rc) return rc;
+        c->begin("pair_mark", (double)npairs * 20);
+        pair_mark_kernel<<<nblk(npairs, 256), 256, 0, c->stream>>>(npairs, in_b ? kb2 : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, L.bS, c->pair_a.p, c->pair_b.p,
+                                                                  c->qname_off.p, c->qname.p, c->flag.p);
+        c->end(); LAUNCH_CHECK(c);
+        if (optical) return phase_optical(c, npairs, in_b ? kb2 : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, L.bS);
+    }
+    return optical ? phase_optical(c, 0, nullptr, nullptr, 0) : E_OK;
+}
+
 int phase_markdup(elp_ctx* c, bool optical) {
     int rc = phase_adapt(c);
     if (rc) return rc;
-    const uint64_t n = c->n;
-    if (n == 0 || c->h_ranges.n_entering == 0) return optical ? phase_optical(c, 0, nullptr, nullptr, 0) : E_OK;
+    // several GPUs (comm.cu): common key ranges, then the visiting mates of cross-group pairs arrive as ghost reads n .. n + n_ghost - 1.
+    // Every rank makes the same collective calls in the same order, whatever its own reads look like.
+    rc = comm_allreduce_ranges(c);
+    if (rc) return rc;
+    rc = spread_exchange_begin(c);
+    if (rc) return rc;
+    const uint64_t n = c->n, nt = n + c->n_ghost;
     const DeviceRanges& R = c->h_ranges;
-    CUDA_TRY(c, c->keys_a.reserve(2 * n + 4, c->stream)); CUDA_TRY(c, c->keys_b.reserve(2 * n + 4, c->stream));
-    CUDA_TRY(c, c->vals_a.reserve(n + 4, c->stream)); CUDA_TRY(c, c->vals_b.reserve(n + 4, c->stream));
-    const int bR = bits_for((uint64_t)c->n_contigs), bL = bits_for((uint64_t)c->n_lib + 1);
-    const int bU = bits_for((uint64_t)((int64_t)R.upos_max - (int64_t)R.upos_min));
-    // ---- fragments (classifyFragment) ----
-    {
-        FragLayout L{}; L.bS = bits_for((uint64_t)R.score_max); L.bU = bU; L.bR = bR; L.bL = bL; L.upos_min = R.upos_min; L.score_max = R.score_max;
-        L.key_bits = L.bS + 2 + L.bU + L.bR + L.bL;
-        if (L.key_bits > 64) return c->fail(E_LIMIT, "fragment signature needs %d bits (>64): too many contigs/libraries for the packed key", L.key_bits);
-        c->begin("frag_keys", (double)n * (2 + 4 + 4 + 4 + 4 + 8 + 4));
-        frag_keys_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->flag.p, c->refid.p, c->rg.p, c->d_rg_lib, c->n_rg, c->upos.p, c->score.p, L, c->keys_a.p, c->vals_a.p);
-        c->end(); LAUNCH_CHECK(c);
-        bool in_b = false;
-        rc = radix_sort_u64(c, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, L.key_bits, &in_b, "u64");
-        if (rc) return rc;
-        const uint64_t m = R.n_entering;
-        c->begin("frag_mark", (double)m * 12);
-        frag_mark_kernel<<<nblk(m, 256), 256, 0, c->stream>>>(m, in_b ? c->keys_b.p : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, L.bS, c->qname_off.p, c->qname.p, c->flag.p);
-        c->end(); LAUNCH_CHECK(c);
+    int rc_body = E_OK;
+    if (nt == 0 || (R.n_entering == 0 && c->n_ghost == 0)) rc_body = optical ? phase_optical(c, 0, nullptr, nullptr, 0) : E_OK;
+    else {
+        rc_body = [&]() -> int {
+            CUDA_TRY(c, c->keys_a.reserve(2 * nt + 4, c->stream)); CUDA_TRY(c, c->keys_b.reserve(2 * nt + 4, c->stream));
+            CUDA_TRY(c, c->vals_a.reserve(nt + 4, c->stream)); CUDA_TRY(c, c->vals_b.reserve(nt + 4, c->stream));
+            const int bR = bits_for((uint64_t)c->n_contigs), bL = bits_for((uint64_t)c->n_lib + 1);
+            const int bU = bits_for((uint64_t)((int64_t)R.upos_max - (int64_t)R.upos_min));
+            // ---- fragments (classifyFragment): local reads only ----
+            if (n && R.n_entering) {
+                FragLayout L{}; L.bS = bits_for((uint64_t)R.score_max); L.bU = bU; L.bR = bR; L.bL = bL; L.upos_min = R.upos_min; L.score_max = R.score_max;
+                L.key_bits = L.bS + 2 + L.bU + L.bR + L.bL;
+                if (L.key_bits > 64) return c->fail(E_LIMIT, "fragment signature needs %d bits (>64): too many contigs/libraries for the packed key", L.key_bits);
+                c->begin("frag_keys", (double)n * (2 + 4 + 4 + 4 + 4 + 8 + 4));
+                frag_keys_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->flag.p, c->refid.p, c->rg.p, c->d_rg_lib, c->n_rg, c->upos.p, c->score.p, L, c->keys_a.p, c->vals_a.p);
+                c->end(); LAUNCH_CHECK(c);
+                bool in_b = false;
+                int r2 = radix_sort_u64(c, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, L.key_bits, &in_b, "u64");
+                if (r2) return r2;
+                const uint64_t m = R.n_entering;
+                c->begin("frag_mark", (double)m * 12);
+                frag_mark_kernel<<<nblk(m, 256), 256, 0, c->stream>>>(m, in_b ? c->keys_b.p : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, L.bS, c->qname_off.p, c->qname.p, c->flag.p);
+                c->end(); LAUNCH_CHECK(c);
+            }
+            return mark_pairs(c, optical, nt, (uint64_t)R.n_true_pairs + c->n_ghost, bU, bR, bL);
+        }();
     }
-    // ---- pairs (classifyPair) ----
-    if (R.n_true_pairs >= 2) {
-        CUDA_TRY(c, c->mate.reserve(n + 4, c->stream));
-        c->begin("join_keys", (double)n * (2 + 8 + 8 + 4 + 4));
-        join_keys_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->flag.p, c->qhash.p, c->keys_a.p, c->vals_a.p, c->mate.p);
-        c->end(); LAUNCH_CHECK(c);
-        bool in_b = false;
-        rc = radix_sort_u64(c, c->keys_a.p, c->keys_b.p, c->vals_a.p, c->vals_b.p, n, 32, &in_b, "u64");   // 31 hash bits + 1: runs of equal hash are verified on bytes anyway
-        if (rc) return rc;
-        const uint64_t m = R.n_true_pairs;
-        c->begin("join", (double)m * 12);
-        join_kernel<<<nblk(m, 256), 256, 0, c->stream>>>(m, in_b ? c->keys_b.p : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, c->rg.p, c->d_rg_lib, c->n_rg, c->qname_off.p, c->qname.p, c->mate.p);
-        c->end(); LAUNCH_CHECK(c);
-        // deterministic pair list, ordered by the arrival of the later mate
-        CUDA_TRY(c, c->scan_tmp.reserve(n + 4, c->stream));
-        uint64_t* slot = c->keys_b.p;   // n+1 u64, free at this point
-        c->begin("pair_flag", (double)n * 8);
-        pair_flag_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->mate.p, c->scan_tmp.p);
-        c->end(); LAUNCH_CHECK(c);
-        rc = exclusive_scan_u32_to_u64(c, c->scan_tmp.p, slot, n);
-        if (rc) return rc;
-        uint64_t npairs = 0;
-        CUDA_TRY(c, cudaMemcpyAsync(&npairs, slot + n, 8, cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-        if (npairs >= (optical ? 1u : 2u)) {
-            CUDA_TRY(c, c->pair_a.reserve(npairs + 4, c->stream)); CUDA_TRY(c, c->pair_b.reserve(npairs + 4, c->stream));
-            PairLayout L{}; L.bS = bits_for((uint64_t)R.score_max * 2); L.bU = bU; L.bR = bR; L.bL = bL; L.upos_min = R.upos_min; L.score_max = R.score_max * 2;
-            L.key_bits = L.bS + 2 * L.bU + 2 + 2 * L.bR + L.bL;
-            if (L.key_bits > 128) return c->fail(E_LIMIT, "pair signature needs %d bits (>128)", L.key_bits);
-            // 128-bit keys live in keys_a as (lo,hi) pairs; slot[] occupies keys_b, so sort into a separate buffer
-            CUDA_TRY(c, c->bytes_tmp.reserve((size_t)npairs * 16 + 64, c->stream));
-            uint64_t* kb2 = reinterpret_cast<uint64_t*>(c->bytes_tmp.p);
-            c->begin("pair_keys", (double)n * 12 + (double)npairs * (2 * 18 + 16 + 12));
-            pair_keys_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(n, c->mate.p, slot, c->flag.p, c->refid.p, c->rg.p, c->d_rg_lib, c->n_rg, c->upos.p, c->score.p, L,
-                                                                  c->keys_a.p, c->vals_a.p, c->pair_a.p, c->pair_b.p);
-            c->end(); LAUNCH_CHECK(c);
-            rc = radix_sort_u128(c, c->keys_a.p, kb2, c->vals_a.p, c->vals_b.p, npairs, L.key_bits, &in_b, "u128");
-            if (rc) return rc;
-            c->begin("pair_mark", (double)npairs * 20);
-            pair_mark_kernel<<<nblk(npairs, 256), 256, 0, c->stream>>>(npairs, in_b ? kb2 : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, L.bS, c->pair_a.p, c->pair_b.p,
-                                                                      c->qname_off.p, c->qname.p, c->flag.p);
-            c->end(); LAUNCH_CHECK(c);
-            if (optical) return phase_optical(c, npairs, in_b ? kb2 : c->keys_a.p, in_b ? c->vals_b.p : c->vals_a.p, L.bS);
-        }
-    }
-    return optical ? phase_optical(c, 0, nullptr, nullptr, 0) : E_OK;
+    rc = spread_exchange_end(c);       // (also when the body failed: the other ranks are waiting in the same exchange)
+    return rc_body ? rc_body : rc;
 }

@@ -192,6 +192,31 @@ class Context:
         t = np.ascontiguousarray(t, dtype=np.int64)
         self._ck(self.L.elp_bqsr_tables_put(self.h, _vp(t), t.size))
 
+    # ---- several GPUs: NCCL behind the C ABI (elprep_b200/csrc/comm.cu) ----
+    @staticmethod
+    def comm_unique_id():
+        """rank 0: the 128-byte NCCL id every rank passes to comm_init (ship it with any host channel)"""
+        L = _lib.load()
+        buf = (C.c_uint8 * 128)()
+        rc = L.elp_comm_unique_id(buf)
+        if rc != 0:
+            raise ElprepError(rc, "elp_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        return bytes(buf)
+
+    def comm_init(self, unique_id, rank, world):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self.L.elp_comm_init(self.h, buf, rank, world))
+
+    def comm_set_partition(self, contig_owner):
+        o = np.ascontiguousarray(contig_owner, dtype=np.int32)
+        self._ck(self.L.elp_comm_set_partition(self.h, _vp(o)))
+
+    def tables_allreduce(self):
+        self._ck(self.L.elp_bqsr_tables_allreduce(self.h))
+
+    def optical_allreduce(self):
+        self._ck(self.L.elp_optical_allreduce(self.h))
+
     def tables_clear(self):
         self._ck(self.L.elp_bqsr_tables_clear(self.h))
 

@@ -167,3 +167,23 @@ def merge_spread_metrics(ctx, spread_metrics):
     for slot, m in enumerate(spread_metrics or []):
         counters = [m[k] if k in PAIR_LEVEL else 0 for k in _lib.ElpDupMetrics.COUNTERS]   # (per-read counters stay 0)
         ctx.optical_merge(slot, counters, m["hist"])
+
+
+def redistribute(batch, owner, rank, world, gather_objects):
+    """The `split` step of an sfm run for one rank's share of the input (sam/split-merge.go:178-311): reads whose contig belongs to another
+    rank are handed to that rank, reads arriving from the others are appended.  Unmapped reads (REFID -1) stay where they are.  Host-side
+    setup (numpy + one object all-gather), not part of any timed region: the device library starts from reads that are already home."""
+    refid = batch.refid
+    dest = np.where(refid >= 0, owner[np.maximum(refid, 0)], rank)
+    out = {}
+    for dst in range(world):
+        if dst != rank:
+            sel = np.nonzero(dest == dst)[0]
+            if sel.size:
+                out[dst] = _pack(batch.take(sel))
+    inbox = gather_objects(out)
+    parts = [batch.take(np.nonzero(dest == rank)[0])]
+    for src in range(world):
+        if src != rank and rank in inbox[src]:
+            parts.append(_unpack(inbox[src][rank]))
+    return sam.AlignmentBatch.concat(parts) if len(parts) > 1 else parts[0]

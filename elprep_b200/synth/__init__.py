@@ -36,7 +36,8 @@ class _Params(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("n_pairs", C.c_int64), ("n_contigs", C.c_int32), ("contig_len", C.c_void_p), ("L", C.c_int32),
                 ("dup_frac", C.c_double), ("optical_frac", C.c_double), ("unmapped_frac", C.c_double), ("mate_unmapped_frac", C.c_double),
                 ("secondary_frac", C.c_double), ("supplementary_frac", C.c_double), ("cross_contig_frac", C.c_double),
-                ("n_rg", C.c_int32), ("wide_quals", C.c_int32), ("exome", C.c_int32), ("threads", C.c_int32)]
+                ("n_rg", C.c_int32), ("wide_quals", C.c_int32), ("exome", C.c_int32), ("threads", C.c_int32),
+                ("home", C.c_void_p), ("pair_id_base", C.c_uint64), ("genome_seed", C.c_uint64)]
 
 
 _lib = None
@@ -70,12 +71,18 @@ def make_header(contigs, n_rg=4):
 
 def make_workload(n_pairs, contigs, seed=20260924, L=150, dup_frac=0.10, optical_frac=0.20, unmapped_frac=0.01,
                   mate_unmapped_frac=0.005, secondary_frac=0.005, supplementary_frac=0.005, cross_contig_frac=0.01,
-                  n_rg=4, wide_quals=False, exome=False, threads=None, want_reference=True):
+                  n_rg=4, wide_quals=False, exome=False, threads=None, want_reference=True, home=None, pair_id_base=0, genome_seed=None, reference_for=None):
+    """home: bool per contig -- fragments start only on those contigs (one generator per contig group of ONE genome: the mates of its
+    cross-contig pairs land on any contig, so pairs span the groups as in a real `elprep sfm` split); pair_id_base keeps QNAMEs unique across
+    the generators; genome_seed: the shared reference genome; reference_for: contig indices whose reference / known sites are returned."""
     lib = _L()
     threads = threads or min(32, os.cpu_count() or 1)
     clen = np.array([ln for _, ln in contigs], dtype=np.int32)
+    home_a = np.ascontiguousarray(home, dtype=np.uint8) if home is not None else None
+    gseed = int(genome_seed) if genome_seed is not None else int(seed)
     p = _Params(seed, n_pairs, len(contigs), clen.ctypes.data_as(C.c_void_p), L, dup_frac, optical_frac, unmapped_frac,
-                mate_unmapped_frac, secondary_frac, supplementary_frac, cross_contig_frac, n_rg, int(wide_quals), int(exome), threads)
+                mate_unmapped_frac, secondary_frac, supplementary_frac, cross_contig_frac, n_rg, int(wide_quals), int(exome), threads,
+                home_a.ctypes.data_as(C.c_void_p) if home_a is not None else None, int(pair_id_base), gseed)
     rec0 = np.zeros(n_pairs + 1, dtype=np.int64)
     cig0 = np.zeros(n_pairs + 1, dtype=np.uint64)
     qn0 = np.zeros(n_pairs + 1, dtype=np.uint64)
@@ -95,13 +102,16 @@ def make_workload(n_pairs, contigs, seed=20260924, L=150, dup_frac=0.10, optical
     bases, sites = None, None
     if want_reference:
         bases, sites = [], []
+        want = set(range(len(contigs))) if reference_for is None else set(reference_for)
         for ci, (_, ln) in enumerate(contigs):
+            if ci not in want:
+                bases.append(None); sites.append(np.zeros((0, 2), np.int32)); continue
             b = np.empty(ln, dtype=np.uint8)
-            lib.synth_genome(C.c_uint64(seed), C.c_int32(ci), C.c_int64(0), C.c_int64(ln), vp(b), C.c_int32(threads))
+            lib.synth_genome(C.c_uint64(gseed), C.c_int32(ci), C.c_int64(0), C.c_int64(ln), vp(b), C.c_int32(threads))
             bases.append(b)
             cap = ln // 1000 + 2
             se = np.zeros(2 * cap, dtype=np.int32)
-            k = lib.synth_known_sites(C.c_uint64(seed), C.c_int32(ci), C.c_int32(ln), vp(se), C.c_int64(cap))
+            k = lib.synth_known_sites(C.c_uint64(gseed), C.c_int32(ci), C.c_int32(ln), vp(se), C.c_int64(cap))
             sites.append(se[:2 * k].reshape(-1, 2).copy())
     return Workload(header, batch, bases, sites, dict(n_pairs=n_pairs, seed=seed, L=L, contigs=contigs))
 

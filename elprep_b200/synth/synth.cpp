@@ -31,6 +31,9 @@ struct Params {
     double dup_frac, optical_frac, unmapped_frac, mate_unmapped_frac, secondary_frac, supplementary_frac, cross_contig_frac;
     int32_t n_rg; int32_t wide_quals; int32_t exome; int32_t first_refid;  // first_refid: refid offset (always 0 here)
     int32_t threads;
+    const uint8_t* home;        // per contig: 1 = fragments start here (nullptr: everywhere); mates of cross-contig pairs may land on any contig
+    uint64_t pair_id_base;      // added to the pair index in QNAMEs (several generators -> one name space)
+    uint64_t genome_seed;       // seed of the reference genome (shared by the generators of one genome)
 };
 
 inline uint8_t genome_base(uint64_t seed, int32_t contig, int64_t pos0) {  // 0-based
@@ -45,7 +48,7 @@ struct Gen {
     Params P; std::vector<double> cum; double total_len;
     explicit Gen(const Params& p) : P(p) {
         cum.resize(p.n_contigs + 1); cum[0] = 0;
-        for (int i = 0; i < p.n_contigs; i++) cum[i + 1] = cum[i] + (double)p.contig_len[i];
+        for (int i = 0; i < p.n_contigs; i++) cum[i + 1] = cum[i] + ((!p.home || p.home[i]) ? (double)p.contig_len[i] : 0.0);
         total_len = cum[p.n_contigs];
     }
     PairClass classify(int64_t p) const {
@@ -139,13 +142,13 @@ struct PairGen {
 
     int qname(int64_t p, const PairClass& c, int64_t root, char* buf) const {
         // SYN:<run>:FC1:<lane>:<tile>:<x>:<y>  (7 fields: tile,x,y = fields 4,5,6; mark-optical-duplicates.go:50-71)
-        uint64_t key = (uint64_t)(c.optical ? root : p);
+        uint64_t key = (uint64_t)(c.optical ? root : p) + G.P.pair_id_base;
         uint64_t v = (key * 0x9E3779B97F4A7C15ULL) & ((1ULL << 40) - 1);
         int lane = 1 + (int)(v & 3), tile = 1101 + (int)((v >> 2) & 1023), x = 1 + (int)((v >> 12) & 0x3fff), y = 1 + (int)((v >> 26) & 0x3fff);
         if (c.optical) {  // same tile, within 50 px of the origin; the run field keeps the name unique
             Rng r(G.P.seed, (uint64_t)p, 7);
             x += (int)r.below(50); y += (int)r.below(50);
-            return std::snprintf(buf, 64, "SYN:%lld:FC1:%d:%d:%d:%d", (long long)(p + 2), lane, tile, x, y);
+            return std::snprintf(buf, 64, "SYN:%lld:FC1:%d:%d:%d:%d", (long long)(p + 2 + (int64_t)G.P.pair_id_base), lane, tile, x, y);
         }
         return std::snprintf(buf, 64, "SYN:1:FC1:%d:%d:%d:%d", lane, tile, x, y);
     }
@@ -157,7 +160,7 @@ struct PairGen {
         int ri = 0; int64_t ref0 = (int64_t)s.pos - 1;
         for (int k = 0; k < s.ncig; k++) {
             int ln = (int)(s.cig[k] >> 4); int op = (int)(s.cig[k] & 15);
-            if (op == 0) { for (int q = 0; q < ln; q++, ri++, ref0++) { bool in_frag = (ref0 + 1) >= frag_lo && (ref0 + 1) <= frag_hi; bases[ri] = in_frag ? genome_base(P.seed, contig, ref0) : (uint8_t)"ACGT"[r.next() & 3]; } }
+            if (op == 0) { for (int q = 0; q < ln; q++, ri++, ref0++) { bool in_frag = (ref0 + 1) >= frag_lo && (ref0 + 1) <= frag_hi; bases[ri] = in_frag ? genome_base(P.genome_seed, contig, ref0) : (uint8_t)"ACGT"[r.next() & 3]; } }
             else if (op == 2) ref0 += ln;
             else { for (int q = 0; q < ln; q++, ri++) bases[ri] = (uint8_t)"ACGT"[r.next() & 3]; }
         }
@@ -264,13 +267,14 @@ struct synth_params {
     uint64_t seed; int64_t n_pairs; int32_t n_contigs; const int32_t* contig_len; int32_t L;
     double dup_frac, optical_frac, unmapped_frac, mate_unmapped_frac, secondary_frac, supplementary_frac, cross_contig_frac;
     int32_t n_rg, wide_quals, exome, threads;
+    const uint8_t* home; uint64_t pair_id_base, genome_seed;
 };
 
 static Params to_params(const synth_params* sp) {
     Params P{}; P.seed = sp->seed; P.n_pairs = sp->n_pairs; P.n_contigs = sp->n_contigs; P.contig_len = sp->contig_len; P.L = sp->L;
     P.dup_frac = sp->dup_frac; P.optical_frac = sp->optical_frac; P.unmapped_frac = sp->unmapped_frac; P.mate_unmapped_frac = sp->mate_unmapped_frac;
     P.secondary_frac = sp->secondary_frac; P.supplementary_frac = sp->supplementary_frac; P.cross_contig_frac = sp->cross_contig_frac;
-    P.n_rg = sp->n_rg; P.wide_quals = sp->wide_quals; P.exome = sp->exome; P.threads = sp->threads; return P;
+    P.n_rg = sp->n_rg; P.wide_quals = sp->wide_quals; P.exome = sp->exome; P.threads = sp->threads; P.home = sp->home; P.pair_id_base = sp->pair_id_base; P.genome_seed = sp->genome_seed ? sp->genome_seed : sp->seed; return P;
 }
 
 // pass 1: per-pair sizes -> totals; pair_rec0/pair_cig0/pair_qn0 are exclusive prefix sums (length n_pairs+1)

@@ -195,6 +195,24 @@ int elp_bqsr_tables_add_elrecal(elp_ctx *ctx, const char *path);
 int elp_optical_write_gob(elp_ctx *ctx, const char *path);
 int elp_optical_add_gob(elp_ctx *ctx, const char *path);
 
+/* ---- several GPUs of one box: one context per GPU (one process or thread each), reads partitioned by contig group the way
+ * `elprep sfm` splits its input (computeContigGroups, sam/split-merge.go:178-213; cmd/sfm.go:605-805).  NCCL is loaded at run time.
+ *   elp_comm_unique_id     rank 0 creates the id and hands it to the other ranks by any means (ncclGetUniqueId)
+ *   elp_comm_init          collective: every rank with the same id, its rank and the world size (ncclCommInitRank on the context's device)
+ *   elp_comm_set_partition contig_owner[n_contigs]: the rank that holds the reads of each contig (unmapped reads may sit anywhere)
+ * With a communicator and a partition set, elp_sort_markdup becomes collective: the mates of pairs that span two ranks -- the reference's
+ * "spread" reads (sam/split-merge.go:286-293) -- are exchanged as 128-byte records (grouped ncclSend / ncclRecv), classified on the rank that owns
+ * the smaller REFID together with its own pairs, and their 0x400 bits are sent back.  elp_bqsr_tables_allreduce is LoadAndCombineBQSRTables
+ * (filters/print-bqsr.go:310-329) as one ncclAllReduce(sum, int64) between elp_bqsr_gather and elp_bqsr_finalize; elp_optical_allreduce is
+ * mergeDuplicatesCtrMaps (filters/mark-optical-duplicates.go:451-466) over the ranks.  Output order = the ranks' outputs concatenated in
+ * contig-group order (MergeSortedFilesSplitPerChromosome, sam/split-merge.go:465-547). */
+int elp_comm_unique_id(uint8_t id[128]);
+int elp_comm_init(elp_ctx *ctx, const uint8_t id[128], int rank, int world);
+int elp_comm_set_partition(elp_ctx *ctx, const int32_t *contig_owner);
+int elp_comm_destroy(elp_ctx *ctx);
+int elp_bqsr_tables_allreduce(elp_ctx *ctx);
+int elp_optical_allreduce(elp_ctx *ctx);
+
 /* ---- phase 4: FinalizeBQSRTables + PrintBQSRTables (filters/bqsr.go:677-694, filters/print-bqsr.go:269-298).
  * report_path may be NULL (no report). Also builds the apply look-up table. ---- */
 int elp_bqsr_finalize(elp_ctx *ctx, const char *report_path);
