@@ -285,19 +285,25 @@ def main():
     ctx2 = make_ctx()
     cs = (ctx, ctx2)
 
+    trace = {}
+
+    def timed(name, fn):
+        t0 = time.perf_counter(); fn(); trace[name] = trace.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+
     def e2e_run(k_steps):
         for s in range(k_steps + 1):
             cur = cs[s % 2] if s < k_steps else None
             prev = cs[(s - 1) % 2] if s >= 1 else None
             if cur is not None:
-                cur.reset(); cur.append_async(hb)
+                timed("reset+append_async", lambda: (cur.reset(), cur.append_async(hb)))
             if prev is not None:
-                phases(prev); prev.fetch_async(out_np)
+                timed("phases", lambda: phases(prev)); timed("fetch_async", lambda: prev.fetch_async(out_np))
             if cur is not None:
-                cur.append_wait()
+                timed("append_wait", cur.append_wait)
             if prev is not None:
-                prev.fetch_wait()
+                timed("fetch_wait", prev.fetch_wait)
     e2e_run(2)                                   # warm-up (allocations of the second context)
+    trace.clear()
     barrier(ctx); ctx2.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -368,7 +374,8 @@ def main():
             "config": {"workload": workload_name, "cpu_arm": f"CPU arm runs a sample: the first {args.cpu_sample} reads per step", "reads_per_gpu": n_reads, "parallelism": f"contig-group x{world}; NCCL inside the C ABI: spread-pair exchange (ncclSend/Recv) in elp_sort_markdup + one ncclAllReduce of the BQSR tables", "flush": "inputs >> L2 (re-ingested every step)"},
             "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
                     "how": "K steps through elp_append_batch_async / phases / elp_fetch_async with pinned host buffers, software-pipelined over two contexts (upload of step s overlaps phases + download of step s-1)",
-                    "unpipelined_ms_per_step": float(np.mean(in_ms) + np.mean(dev_ms) + np.mean(out_ms))},
+                    "unpipelined_ms_per_step": float(np.mean(in_ms) + np.mean(dev_ms) + np.mean(out_ms)),
+                    "host_ms_per_step_in_call": {k: v / args.steps for k, v in trace.items()}},
             "phases_per_rank": phases_per_rank, "roofline_graded": graded,
             "gpu_launches": launches, "verified": (verified or {}).get("ok"), "verify": verified, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": kern}
     print(json.dumps(line))

@@ -75,6 +75,31 @@ template <class T> int grow(elp_ctx* c, DBuf<T>& b, size_t need, size_t keep) {
 
 }  // namespace
 
+// Small host->device uploads INSIDE the phases (value ranges, look-up tables, ...) do not go through the copy engine: it serves its queue in
+// order, so behind the multi-gigabyte upload of another context of a pipelined caller they would wait for all of it.  The bytes are staged in
+// page-locked host memory that the GPU can address, and a kernel pulls them across.
+__global__ void __launch_bounds__(256) pull_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    if (i + 16 <= n) *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+    else for (size_t k = i; k < n; k++) dst[k] = src[k];
+}
+int upload_small(elp_ctx* c, void* dst, const void* src, size_t bytes) {
+    constexpr size_t CAP = 8u << 20;
+    if (!bytes) return E_OK;
+    if (bytes > CAP || (reinterpret_cast<uintptr_t>(dst) & 15)) { CUDA_TRY(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream)); return E_OK; }
+    if (!c->h_stage) CUDA_TRY(c, cudaHostAlloc(&c->h_stage, CAP, cudaHostAllocPortable | cudaHostAllocMapped));
+    if (c->stage_off + bytes > CAP) { CUDA_TRY(c, cudaStreamSynchronize(c->stream)); c->stage_off = 0; }
+    uint8_t* st = reinterpret_cast<uint8_t*>(c->h_stage) + c->stage_off;
+    memcpy(st, src, bytes);
+    void* dev_src = st;
+    CUDA_TRY(c, cudaHostGetDevicePointer(&dev_src, st, 0));
+    c->launches++;
+    pull_kernel<<<(unsigned)((bytes + 16 * 256 - 1) / (16 * 256)), 256, 0, c->stream>>>(reinterpret_cast<uint8_t*>(dst), reinterpret_cast<const uint8_t*>(dev_src), bytes);
+    LAUNCH_CHECK(c);
+    c->stage_off += (bytes + 255) & ~(size_t)255;
+    return E_OK;
+}
+
 int qual_presence_update(elp_ctx* c, uint64_t first_byte, uint64_t n_bytes) {
     if (!n_bytes) return E_OK;
     const unsigned grid = (unsigned)std::min<uint64_t>((n_bytes / 16 + 255) / 256 + 1, 148 * 16);
@@ -174,7 +199,7 @@ void elp_destroy(elp_ctx* c) {
     for (auto p : c->d_refhot_raw) if (p) cudaFree(p);
     for (auto p : c->d_sites) if (p) cudaFree(p);
     void* singles[] = {c->d_rg_lib, c->d_rg_cov, c->d_contig_len, c->d_ranges, c->d_err, (void*)c->d_ref_ptrs, (void*)c->d_refnib_ptrs, (void*)c->d_refhot_ptrs, c->d_bq_small, c->d_qpresent, c->d_ref_len, (void*)c->d_site_ptrs, c->d_n_sites, c->d_tables,
-                       c->d_lut, c->d_cov_exists, c->d_opt_ctr, c->d_opt_hist, c->d_opt_ovf, c->d_opt_small, c->d_rg_names, c->d_rg_name_off, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
+                       c->d_lut, c->d_clut, c->d_rowtab, c->d_cov_exists, c->d_opt_ctr, c->d_opt_hist, c->d_opt_ovf, c->d_opt_small, c->d_rg_names, c->d_rg_name_off, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
     for (void* p : singles) if (p) cudaFree(p);
     c->refid.release(); c->pos.release(); c->nref.release(); c->pnext.release(); c->tlen.release(); c->rg.release(); c->flag.release(); c->mapq.release();
     c->qname_off.release(); c->cigar_off.release(); c->qual_off.release(); c->seq_off.release(); c->qname.release(); c->seq.release(); c->qual.release(); c->cigar.release();
@@ -188,6 +213,7 @@ void elp_destroy(elp_ctx* c) {
     elp_comm_destroy(c);
     if (c->d_owner) cudaFree(c->d_owner);
     c->sp_sendbuf.release(); c->sp_recvbuf.release(); c->sp_sent_idx.release();
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     if (c->copy_in) { cudaStreamDestroy(c->copy_in); cudaEventDestroy(c->ev_in); cudaEventDestroy(c->ev_staged); }
     if (c->copy_out) { cudaStreamDestroy(c->copy_out); cudaEventDestroy(c->ev_out); }
     if (c->stream) cudaStreamDestroy(c->stream);

@@ -20,7 +20,7 @@
 #define CNT_MINB 2
 #endif
 #ifndef CNT_STAGES_N
-#define CNT_STAGES_N 3
+#define CNT_STAGES_N 2
 #endif
 // software pipeline of a warp: records are fetched CNT_D2 iterations, windows CNT_D2 - CNT_D1 iterations ahead of their use; CNT_WN copy groups stay in flight
 constexpr int CNT_WARPS = 8, CNT_STAGES = CNT_STAGES_N, CNT_WN = CNT_STAGES - 1, CNT_D1 = CNT_WN + 1, CNT_D2 = 2 * CNT_WN + 1, CNT_RECRING = CNT_D2 + 1, SEG_PASSES = 255, MAX_CLS = 64;
@@ -159,6 +159,7 @@ struct CountArgs {
     unsigned long long* tables; TableGeom geom;
     int lpr, rpw; uint32_t sh, lut_lo, lut_hi; uint8_t slot_q[4];
     uint32_t rec_bytes;             // ring slot of one pass' records: 32 * rpw
+    int n_cls; uint32_t mm_cells;   // CTA-private mismatch tables in shared memory (0: straight to the global table)
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_shared, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory"); }
@@ -175,6 +176,15 @@ __global__ void __launch_bounds__(CNT_WARPS * 32, CNT_MINB) bqsr_count_kernel(Co
     if (threadIdx.x < 33) s_rt[threadIdx.x] = lanes::range_plane((int)threadIdx.x);
     __syncthreads();
     const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
+    // mismatches are sparse but pile up on few cells (a low QUAL value's 16 contexts take most of them): privatised per CTA in shared memory
+    // -- global atomics on ~100 hot addresses serialise in L2 and were what bounded the first version of this kernel
+    uint32_t* mm_cyc = reinterpret_cast<uint32_t*>(cnt_smem + (size_t)CNT_WARPS * WARP_BYTES);       // [n_cls][S][32 * lpr]
+    const int Lpad = 32 * A.lpr;
+    uint32_t* mm_ctx = mm_cyc + (size_t)A.n_cls * S * Lpad;                                          // [n_cls / 2][S][16]
+    const bool mm_sh = A.mm_cells != 0;
+    if (mm_sh) for (uint32_t i = threadIdx.x; i < A.mm_cells; i += blockDim.x) mm_cyc[i] = 0;
+    __syncthreads();
+    const uint32_t mm_cyc_s = (uint32_t)__cvta_generic_to_shared(mm_cyc), mm_ctx_s = (uint32_t)__cvta_generic_to_shared(mm_ctx);
     const uint32_t wbase = (uint32_t)__cvta_generic_to_shared(cnt_smem) + warp * WARP_BYTES;
     const uint32_t rbase = wbase + CNT_STAGES * STAGE_BYTES;
     const uint32_t rt_addr = (uint32_t)__cvta_generic_to_shared(s_rt);
@@ -329,10 +339,13 @@ __global__ void __launch_bounds__(CNT_WARPS * 32, CNT_MINB) bqsr_count_kernel(Co
                             const int b = __ffs((int)ms) - 1; ms &= ms - 1;
                             const int t = lanes::plane_base(b);
                             const int q = A.slot_q[s];
-                            red_add_u64(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_cycle(sign * (i0 + t + 1))) + 1, 1ull);
-                            if ((okc >> b) & 1u) {
-                                const int ctx = (int)(((p0 >> b) & 1u) | (((p1 >> b) & 1u) << 1) | (((c0 >> b) & 1u) << 2) | (((c1 >> b) & 1u) << 3));
-                                red_add_u64(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_ctx(ctx)) + 1, 1ull);
+                            const int ctx = (int)(((p0 >> b) & 1u) | (((p1 >> b) & 1u) << 1) | (((c0 >> b) & 1u) << 2) | (((c1 >> b) & 1u) << 3));
+                            if (mm_sh) {
+                                asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(mm_cyc_s + 4u * (uint32_t)(((int)cls * S + s) * Lpad + i0 + t)) : "memory");
+                                if ((okc >> b) & 1u) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(mm_ctx_s + 4u * (uint32_t)((cov * S + s) * 16 + ctx)) : "memory");
+                            } else {
+                                red_add_u64(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_cycle(sign * (i0 + t + 1))) + 1, 1ull);
+                                if ((okc >> b) & 1u) red_add_u64(A.tables + 2 * A.geom.idx(cov, q, A.geom.col_ctx(ctx)) + 1, 1ull);
                             }
                         }
                     }
@@ -357,6 +370,21 @@ __global__ void __launch_bounds__(CNT_WARPS * 32, CNT_MINB) bqsr_count_kernel(Co
             uint32_t v = (cx[cell >> 1] >> (16 * (cell & 1))) & 0xffffu;
             v = __reduce_add_sync(FULL_MASK, v);
             if (lane == 0 && v) red_add_u64(A.tables + 2 * A.geom.idx(cov, A.slot_q[cell % S], A.geom.col_ctx(cell / S)), (unsigned long long)v);
+        }
+    }
+    if (mm_sh) {
+        __syncthreads();
+        const uint32_t n_cyc = (uint32_t)(A.n_cls * S * Lpad);
+        for (uint32_t i = threadIdx.x; i < A.mm_cells; i += blockDim.x) {
+            const uint32_t v = mm_cyc[i];
+            if (!v) continue;
+            if (i < n_cyc) {
+                const int t = (int)(i % (uint32_t)Lpad), s = (int)((i / (uint32_t)Lpad) % S), cl = (int)(i / ((uint32_t)Lpad * S));
+                red_add_u64(A.tables + 2 * A.geom.idx(cl >> 1, A.slot_q[s], A.geom.col_cycle(((cl & 1) ? -1 : 1) * (t + 1))) + 1, (unsigned long long)v);
+            } else {
+                const uint32_t k = i - n_cyc; const int ctx = (int)(k & 15u), s = (int)((k >> 4) % S), cv = (int)((k >> 4) / S);
+                red_add_u64(A.tables + 2 * A.geom.idx(cv, A.slot_q[s], A.geom.col_ctx(ctx)) + 1, (unsigned long long)v);
+            }
         }
     }
 }

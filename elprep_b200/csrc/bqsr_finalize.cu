@@ -318,10 +318,42 @@ int build_apply_lut(elp_ctx* c, int Lc) {
         CUDA_TRY(c, cudaMalloc(&c->d_lut, lut.size() + 16));
         c->lut_cap = lut.size() + 16;
     }
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_lut, lut.data(), lut.size(), cudaMemcpyHostToDevice, c->stream));
+    { int rcu = upload_small(c, c->d_lut, lut.data(), lut.size()); if (rcu) return rcu; }
     if (!c->d_cov_exists) CUDA_TRY(c, cudaMalloc(&c->d_cov_exists, std::max(1, g.n_cov)));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_cov_exists, cov_exists.data(), g.n_cov, cudaMemcpyHostToDevice, c->stream));
+    { int rcu = upload_small(c, c->d_cov_exists, cov_exists.data(), g.n_cov); if (rcu) return rcu; }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     c->lut_maxcyc = Lc;
+    c->h_lut.swap(lut);            // kept for the compact shared-memory table (build_compact_lut)
+    c->clut_Lc = 0;                // rebuilt on the next apply
+    return E_OK;
+}
+
+// The apply table compacted for bqsr_apply2_kernel: only the QUAL values >= 6 that occur in the QUAL arena get rows ("slots"); layout
+// [cycle + Lc + 32][covariate][slot][17] with 32 zero cycles of margin on both sides (lanes index up to 31 bases past a read's end) and an
+// odd number of bytes per cycle (bank spread).  Rebuilt whenever the full table or the set of QUAL values changes.
+int build_compact_lut(elp_ctx* c) {
+    uint32_t present[4] = {0, 0, 0, 0};
+    CUDA_TRY(c, cudaMemcpyAsync(present, c->d_qpresent, 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (c->clut_Lc == c->lut_maxcyc && memcmp(present, c->clut_present, 16) == 0) return E_OK;
+    memcpy(c->clut_present, present, 16);
+    c->clut_Lc = 0; c->clut_bytes = 0;
+    std::vector<int> slots;
+    for (int q = 6; q < 94; q++) if ((present[q >> 5] >> (q & 31)) & 1u) slots.push_back(q);
+    const int S = (int)slots.size(), Lc = c->lut_maxcyc, ncyc = 2 * Lc + 1, n_cov = c->geom.n_cov;
+    if (S == 0 || n_cov == 0 || c->h_lut.empty()) return E_OK;
+    uint32_t blk = (uint32_t)(n_cov * S * 17); if (!(blk & 1)) blk++;
+    const size_t bytes = ((size_t)(ncyc + 64) * blk + 15) / 16 * 16;
+    if (bytes > 80 * 1024) return E_OK;                               // too large for two CTAs per SM: the global-memory kernel serves
+    std::vector<uint8_t> t(bytes, 0); std::vector<uint16_t> rowtab(256, 0);
+    for (int sl = 0; sl < S; sl++) rowtab[slots[sl]] = (uint16_t)(sl * 17);
+    for (int cy = 0; cy < ncyc; cy++) for (int cv = 0; cv < n_cov; cv++) for (int sl = 0; sl < S; sl++)
+        memcpy(&t[(size_t)(cy + 32) * blk + (size_t)(cv * S + sl) * 17], &c->h_lut[(((size_t)cv * 94 + slots[sl]) * ncyc + cy) * 17], 17);
+    if (c->clut_cap < bytes) { if (c->d_clut) cudaFree(c->d_clut); c->d_clut = nullptr; CUDA_TRY(c, cudaMalloc(&c->d_clut, bytes)); c->clut_cap = bytes; }
+    if (!c->d_rowtab) CUDA_TRY(c, cudaMalloc(&c->d_rowtab, 512));
+    { int rcu = upload_small(c, c->d_clut, t.data(), bytes); if (rcu) return rcu; }
+    { int rcu = upload_small(c, c->d_rowtab, rowtab.data(), 512); if (rcu) return rcu; }
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->clut_bytes = (uint32_t)bytes; c->clut_blk = blk; c->clut_S17 = (uint32_t)(S * 17); c->clut_Lc = Lc;
     return E_OK;
 }

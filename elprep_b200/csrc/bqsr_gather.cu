@@ -896,8 +896,11 @@ FastPlan plan_fast(const elp_ctx* c, const uint32_t present[4]) {
     return P;
 }
 
-template <int S> int launch_count(elp_ctx* c, const CountArgs& K, bool indel, unsigned grid) {
-    const size_t smem0 = (size_t)CNT_WARPS * (CNT_STAGES * 7 * 512 + CNT_RECRING * K.rec_bytes), smem1 = (size_t)CNT_WARPS * (CNT_STAGES * 9 * 512 + CNT_RECRING * K.rec_bytes);
+template <int S> int launch_count(elp_ctx* c, CountArgs K, bool indel, unsigned grid) {
+    // CTA-private mismatch tables when they are small (<= 24 KB); otherwise the global table takes the (sparse) mismatches directly
+    const size_t mm = ((size_t)K.n_cls * S * 32 * K.lpr + (size_t)(K.n_cls / 2) * S * 16);
+    K.mm_cells = mm * 4 <= 24 * 1024 ? (uint32_t)mm : 0u;
+    const size_t smem0 = (size_t)CNT_WARPS * (CNT_STAGES * 7 * 512 + CNT_RECRING * K.rec_bytes) + (size_t)K.mm_cells * 4, smem1 = (size_t)CNT_WARPS * (CNT_STAGES * 9 * 512 + CNT_RECRING * K.rec_bytes) + (size_t)K.mm_cells * 4;
     if (!indel) {
         CUDA_TRY(c, cudaFuncSetAttribute(bqsr_count_kernel<S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));
         bqsr_count_kernel<S, false><<<grid, CNT_WARPS * 32, smem0, c->stream>>>(K);
@@ -964,7 +967,7 @@ int phase_bqsr_gather(elp_ctx* c) {
             c->launches++; LAUNCH_CHECK(c);
             CountArgs K{};
             K.qual = c->qual.p; K.seq = c->seq.p; K.refhot = c->d_refhot_ptrs; K.recs = c->bq_recs.p; K.tables = A.tables; K.geom = c->geom;
-            K.lpr = lpr; K.rpw = rpw; K.rec_bytes = 32u * (uint32_t)rpw; K.sh = F.sh; K.lut_lo = F.lut_lo; K.lut_hi = F.lut_hi;
+            K.lpr = lpr; K.rpw = rpw; K.rec_bytes = 32u * (uint32_t)rpw; K.n_cls = n_cls; K.sh = F.sh; K.lut_lo = F.lut_lo; K.lut_hi = F.lut_hi;
             for (int s = 0; s < 4; s++) K.slot_q[s] = F.slot_q[s];
             const unsigned grid = (unsigned)sms * CNT_MINB;
             for (int v = 0; v < 2; v++) {

@@ -144,7 +144,7 @@ int comm_allreduce_ranges(elp_ctx* c) {
     NcclApi* N = nccl_api(&c->err); if (!N) return E_CUDA;
     int32_t h[4] = {c->h_ranges.n_entering ? -c->h_ranges.upos_min : INT_MIN, c->h_ranges.n_entering ? c->h_ranges.upos_max : INT_MIN, c->h_ranges.score_max, (int32_t)std::min<uint32_t>(c->h_ranges.n_entering, 1u)};
     CUDA_TRY(c, c->scan_tmp.reserve(16, c->stream));
-    CUDA_TRY(c, cudaMemcpyAsync(c->scan_tmp.p, h, 16, cudaMemcpyHostToDevice, c->stream));
+    { int rcu = upload_small(c, c->scan_tmp.p, h, 16); if (rcu) return rcu; }
     NCCL_TRY(c, N, N->AllReduce(c->scan_tmp.p, c->scan_tmp.p, 4, ncclInt32, ncclMax, (ncclComm_t)c->comm, c->stream));
     CUDA_TRY(c, cudaMemcpyAsync(h, c->scan_tmp.p, 16, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -174,7 +174,7 @@ int spread_exchange_begin(elp_ctx* c) {
     if (n + tot_recv >= (1ull << 32)) return c->fail(E_LIMIT, "more than 2^32-1 reads + visiting mates in one context");
     CUDA_TRY(c, c->sp_sendbuf.reserve(8 * tot_send + 8, s)); CUDA_TRY(c, c->sp_recvbuf.reserve(8 * tot_recv + 8, s)); CUDA_TRY(c, c->sp_sent_idx.reserve(tot_send + 4, s));
     if (tot_send) {
-        CUDA_TRY(c, cudaMemcpyAsync(d_base, base.data(), W * 4, cudaMemcpyHostToDevice, s));
+        { int rcu = upload_small(c, d_base, base.data(), (size_t)W * 4); if (rcu) return rcu; }
         FillArgs A{};
         A.n = n; A.flag = c->flag.p; A.refid = c->refid.p; A.nref = c->nref.p; A.rg = c->rg.p; A.upos = c->upos.p; A.score = c->score.p; A.qhash = c->qhash.p; A.qname_off = c->qname_off.p; A.qname = c->qname.p;
         A.owner = c->d_owner; A.n_contigs = c->n_contigs; A.me = c->rank; A.base = d_base; A.cursor = d_cur; A.recs = c->sp_sendbuf.p; A.sent_idx = c->sp_sent_idx.p; A.err = c->d_err;

@@ -57,6 +57,7 @@ struct elp_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // upload / download streams of the asynchronous append / fetch
     cudaEvent_t ev_in = nullptr, ev_staged = nullptr, ev_out = nullptr;
+    void* h_stage = nullptr; size_t stage_off = 0;        // page-locked staging of upload_small
     std::string err;
     std::mutex append_mu;
     bool profile = false;
@@ -150,6 +151,9 @@ struct elp_ctx {
     int lut_maxcyc = 0;
     size_t lut_cap = 0;
     uint8_t* d_cov_exists = nullptr;          // [n_cov]
+    uint8_t* d_clut = nullptr; uint16_t* d_rowtab = nullptr;   // compact apply table for the shared-memory kernel: [cycle][covariate][slot][17], QUAL -> slot offset
+    uint32_t clut_bytes = 0, clut_blk = 0, clut_S17 = 0; int clut_Lc = 0; size_t clut_cap = 0; uint32_t clut_present[4] = {0, 0, 0, 0};
+    std::vector<uint8_t> h_lut;               // the full apply table [n_cov][94][2*lut_maxcyc+1][17] on the host
 
     // ---- duplication metrics (optical.cu) ----
     void* d_opt_ctr = nullptr; void* d_opt_hist = nullptr; void* d_opt_ovf = nullptr; uint32_t* d_opt_small = nullptr;
@@ -228,9 +232,11 @@ int phase_bqsr_gather(elp_ctx* c);
 int phase_bqsr_finalize(elp_ctx* c, const char* report_path);
 int phase_bqsr_apply(elp_ctx* c);
 int build_apply_lut(elp_ctx* c, int Lc);   // bqsr_finalize.cu
+int build_compact_lut(elp_ctx* c);
 int upload_side_inputs(elp_ctx* c);
 int pack_reference(elp_ctx* c, int contig);
 int check_device_errors(elp_ctx* c);
+int upload_small(elp_ctx* c, void* dst, const void* src, size_t bytes);   // api.cu: host -> device without the copy engine
 int comm_allreduce_ranges(elp_ctx* c);   // comm.cu
 int spread_exchange_begin(elp_ctx* c);
 int spread_exchange_end(elp_ctx* c);

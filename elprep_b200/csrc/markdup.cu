@@ -421,7 +421,7 @@ int phase_adapt(elp_ctx* c) {
     CUDA_TRY(c, c->score.reserve(n + 1, c->stream));
     CUDA_TRY(c, c->qhash.reserve(n + 1, c->stream));
     DeviceRanges init{}; init.pos_max = 0; init.upos_min = INT_MAX; init.upos_max = INT_MIN; init.score_max = 0; init.lseq_max = 0;
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_ranges, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    { int rcu = upload_small(c, c->d_ranges, &init, sizeof init); if (rcu) return rcu; }
     if (n) {
         int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
         AdaptArgs A{};
