@@ -198,6 +198,9 @@ void elp_destroy(elp_ctx* c) {
     for (auto p : c->d_refnib_raw) if (p) cudaFree(p);
     for (auto p : c->d_refhot_raw) if (p) cudaFree(p);
     for (auto p : c->d_sites) if (p) cudaFree(p);
+    for (auto p : c->d_regions) if (p) cudaFree(p);
+    if (c->d_region_ptrs) cudaFree((void*)c->d_region_ptrs);
+    if (c->d_n_regions) cudaFree(c->d_n_regions);
     void* singles[] = {c->d_rg_lib, c->d_rg_cov, c->d_contig_len, c->d_ranges, c->d_err, (void*)c->d_ref_ptrs, (void*)c->d_refnib_ptrs, (void*)c->d_refhot_ptrs, c->d_bq_small, c->d_qpresent, c->d_ref_len, (void*)c->d_site_ptrs, c->d_n_sites, c->d_tables,
                        c->d_lut, c->d_clut, c->d_rowtab, c->d_cov_exists, c->d_opt_ctr, c->d_opt_hist, c->d_opt_ovf, c->d_opt_small, c->d_rg_names, c->d_rg_name_off, c->ws.ghist, c->ws.gofs, c->ws.counters, c->ws.status};
     for (void* p : singles) if (p) cudaFree(p);
@@ -226,7 +229,7 @@ int elp_reset(elp_ctx* c) {
     if (c->copy_in) CUDA_TRY(c, cudaStreamSynchronize(c->copy_in));
     if (c->copy_out) CUDA_TRY(c, cudaStreamSynchronize(c->copy_out));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    c->n = c->n_qname = c->n_cigar = 0; c->n_qual = c->n_seq = ARENA_FRONT_PAD; c->n_bam = c->bam_reads = 0; c->n_filtered = 0;
+    c->n = c->n_qname = c->n_cigar = 0; c->n_qual = c->n_seq = ARENA_FRONT_PAD; c->n_bam = c->bam_reads = 0; c->n_filtered = 0; c->n_cleaned = 0;
     CUDA_TRY(c, cudaMemsetAsync(c->d_qpresent, 0, 16, c->stream));
     c->adapted = c->sorted = c->qual_out_valid = c->gathered = c->finalized = c->opt_valid = false;
     c->launches = 0;

@@ -12,6 +12,7 @@
 // hand them back (elp_fetch_bam): output order, FLAG and QUAL patched, everything else -- names, CIGAR, tags -- untouched
 // (the counterpart of formatting every *sam.Alignment again, sam/bam-files.go:635-735).  Not handled (error return): the CG:B long-CIGAR convention (:376-392),
 // an RG:Z value that is not an @RG ID of the header.
+#include <algorithm>
 #include "ctx.h"
 #include "../../include/elprep_b200.h"
 
@@ -106,8 +107,34 @@ __global__ void __launch_bounds__(256) bam_fixed_kernel(BamArgs A) {
 
 // ---- fused per-record filters of the ingest (filters/simple-filters.go:71-103,332-347) ----
 // keep[i] = 1 iff record i passes every requested predicate; also checks that the caller's offsets follow the block_size chain
+// intervals.Overlap (intervals/intervals.go:146-164) over one contig's flattened, start-sorted (start, end) pairs
+__device__ bool overlap_any(const int32_t* __restrict__ iv, uint64_t n, int32_t start, int32_t end) {
+    int64_t left = 0, right = (int64_t)n - 1;
+    while (left <= right) {
+        const int64_t mid = (left + right) / 2;
+        const int32_t is = iv[2 * mid], ie = iv[2 * mid + 1];
+        if (is > end - 1) right = mid - 1;
+        else if (ie <= start - 1) left = mid + 1;
+        else return true;
+    }
+    return false;
+}
+// integer value of an optional field at r[x] (x behind tag and type), by BAM type; false for a non-integer type
+__device__ __forceinline__ bool tag_int(const uint8_t* r, uint64_t x, uint8_t ty, int64_t* v) {
+    switch (ty) {
+        case 'c': *v = (int8_t)r[x]; return true;
+        case 'C': *v = r[x]; return true;
+        case 's': *v = (int16_t)rd16(r + x); return true;
+        case 'S': *v = rd16(r + x); return true;
+        case 'i': *v = (int32_t)rd32(r + x); return true;
+        case 'I': *v = rd32(r + x); return true;
+        default: return false;
+    }
+}
+
 __global__ void __launch_bounds__(256) bam_keep_kernel(uint64_t n, const uint8_t* __restrict__ raw, const uint64_t* __restrict__ rec_off, uint64_t n_bytes,
-                                                        uint32_t mask, int32_t min_mapq, uint32_t* __restrict__ keep, uint32_t* __restrict__ err) {
+                                                        uint32_t mask, int32_t min_mapq, const int32_t* const* __restrict__ regions, const uint64_t* __restrict__ n_regions, int n_contigs,
+                                                        uint32_t* __restrict__ keep, uint32_t* __restrict__ err) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint64_t st = rec_off[i], len = rec_off[i + 1] - st;
@@ -125,6 +152,50 @@ __global__ void __launch_bounds__(256) bam_keep_kernel(uint64_t n, const uint8_t
         for (uint32_t q = 0; q < n_cig; q++) { const uint32_t o = r[c0 + 4 * q] & 15u; if (o != 0 && o != 4) { k = false; break; } }
     }
     if ((mask & ELP_FILTER_DUPLICATES) && (flag & F_DUPLICATE)) k = false;                                        // RemoveDuplicateReads :131-133 (flags of the input)
+    if (k && (mask & (ELP_FILTER_NON_EXACT_STRICT | ELP_FILTER_TARGET_REGIONS))) {
+        const int32_t l_seq = (int32_t)rd32(r + 20);
+        const uint64_t c0 = BAM_FIXED + (uint64_t)l_name, lsq = l_seq < 0 ? 0ull : (uint64_t)(uint32_t)l_seq;
+        const uint64_t tags0 = c0 + 4ull * n_cig + ((lsq + 1) >> 1) + lsq;
+        if (l_seq < 0 || tags0 > len) { atomicOr(err, DERR_BAM); keep[i] = 0; return; }
+        if (mask & ELP_FILTER_TARGET_REGIONS) {                                                                   // RemoveNonOverlappingReads :310-328
+            int32_t a_end = pos;
+            if (!(flag & F_UNMAPPED)) {
+                int32_t rl = 0, fl = 0;
+                for (uint32_t q = 0; q < n_cig; q++) { const uint32_t op = rd32(r + c0 + 4 * q); const uint32_t o = op & 15u; const int32_t ln = (int32_t)(op >> 4);
+                    if (o == 0 || o == 1 || o == 4 || o == 7 || o == 8) rl += ln; if (o == 0 || o == 2 || o == 3 || o == 7 || o == 8) fl += ln; }
+                if (rl > 0) a_end = pos + fl - 1;                                                                 // aln.End(), sam/sam-types.go:769-775
+            }
+            if (refid < 0 || refid >= n_contigs || !regions || !overlap_any(regions[refid], n_regions[refid], pos, a_end)) k = false;   // no regions for RNAME: Overlap(nil) is false
+        }
+        if (k && (mask & ELP_FILTER_NON_EXACT_STRICT)) {                                                          // RemoveNonExactMappingReadsStrict :115-136: X0=1, X1=0, XM=0, XO=0, XG=0
+            int64_t want[5] = {1, 0, 0, 0, 0}; uint32_t seen = 0; bool good = true;
+            uint64_t x = tags0;
+            while (x + 3 <= len && good) {
+                const uint8_t t0 = r[x], t1 = r[x + 1], ty = r[x + 2];
+                x += 3;
+                int which = -1;
+                if (t0 == 'X') which = t1 == '0' ? 0 : (t1 == '1' ? 1 : (t1 == 'M' ? 2 : (t1 == 'O' ? 3 : (t1 == 'G' ? 4 : -1))));
+                uint64_t sz = 0;
+                switch (ty) {
+                    case 'A': case 'c': case 'C': sz = 1; break;
+                    case 's': case 'S': sz = 2; break;
+                    case 'i': case 'I': case 'f': sz = 4; break;
+                    case 'Z': case 'H': { uint64_t e = x; while (e < len && r[e] != 0) e++; sz = e - x + 1; break; }
+                    case 'B': { if (x + 5 > len) { sz = len; break; } const uint8_t sub = r[x]; const uint64_t cnt = rd32(r + x + 1);
+                                sz = 5 + cnt * ((sub == 'c' || sub == 'C') ? 1 : ((sub == 's' || sub == 'S') ? 2 : 4)); break; }
+                    default: sz = len;                                                                            // malformed: bam_fixed_kernel reports it
+                }
+                if (x + sz > len) break;
+                if (which >= 0 && !(seen & (1u << which))) {                                                      // (TAGS.Get returns the first occurrence)
+                    int64_t v;
+                    seen |= 1u << which;
+                    if (!tag_int(r, x, ty, &v) || v != want[which]) good = false;                                 // a non-integer value is treated as a mismatch (the Go type assertion would panic)
+                }
+                x += sz;
+            }
+            if (!good || seen != 31u) k = false;
+        }
+    }
     keep[i] = k ? 1u : 0u;
 }
 __global__ void __launch_bounds__(256) bam_compact_kernel(uint64_t n, const uint32_t* __restrict__ keep, const uint64_t* __restrict__ slot, const uint64_t* __restrict__ rec_off,
@@ -204,6 +275,19 @@ template <class T> int grow(elp_ctx* c, DBuf<T>& b, size_t need, size_t keep) {
 
 }  // namespace
 
+static int upload_regions(elp_ctx* c) {
+    if (!c->regions_dirty && c->d_region_ptrs) return E_OK;
+    const int nc = std::max(1, c->n_contigs);
+    if ((int)c->d_regions.size() != c->n_contigs) { c->d_regions.assign(c->n_contigs, nullptr); c->n_regions.assign(c->n_contigs, 0); }
+    if (!c->d_region_ptrs) { CUDA_TRY(c, cudaMalloc(&c->d_region_ptrs, nc * sizeof(void*))); CUDA_TRY(c, cudaMalloc(&c->d_n_regions, nc * 8)); }
+    if (c->n_contigs) {
+        CUDA_TRY(c, cudaMemcpy(c->d_region_ptrs, c->d_regions.data(), c->n_contigs * sizeof(void*), cudaMemcpyHostToDevice));
+        CUDA_TRY(c, cudaMemcpy(c->d_n_regions, c->n_regions.data(), c->n_contigs * 8, cudaMemcpyHostToDevice));
+    }
+    c->regions_dirty = false;
+    return E_OK;
+}
+
 extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_bytes, const uint64_t* record_off, uint64_t n_records) {
     if (!c || (!records && n_bytes)) return ELP_EINVAL;
     cudaSetDevice(c->device);
@@ -238,7 +322,8 @@ extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_byt
     if (c->filter_mask || c->filter_min_mapq > 0) {
         TRY(grow(c, c->scan_tmp, nrec + 8, 0)); TRY(grow(c, c->off_stage, nrec + 2, 0));
         c->begin("bam_keep", (double)nrec * 48);
-        bam_keep_kernel<<<nblk(nrec, 256), 256, 0, s>>>(nrec, c->bam_raw.p, c->bam_off.p, n_bytes, c->filter_mask, c->filter_min_mapq, c->scan_tmp.p, c->d_err);
+        if (c->filter_mask & ELP_FILTER_TARGET_REGIONS) { int rcr = upload_regions(c); if (rcr) return rcr; }
+        bam_keep_kernel<<<nblk(nrec, 256), 256, 0, s>>>(nrec, c->bam_raw.p, c->bam_off.p, n_bytes, c->filter_mask, c->filter_min_mapq, c->d_region_ptrs, c->d_n_regions, c->n_contigs, c->scan_tmp.p, c->d_err);
         c->end(); LAUNCH_CHECK(c);
         TRY(exclusive_scan_u32_to_u64(c, c->scan_tmp.p, c->off_stage.p, nrec));
         bam_compact_kernel<<<nblk(nrec, 256), 256, 0, s>>>(nrec, c->scan_tmp.p, c->off_stage.p, c->bam_off.p, c->bam_start.p); c->launches++;
@@ -333,6 +418,7 @@ extern "C" uint64_t elp_fetch_bam_bytes(elp_ctx* c, uint64_t first, uint64_t n) 
 }
 
 extern "C" int elp_fetch_bam(elp_ctx* c, uint64_t first, uint64_t n, uint8_t* out, uint64_t capacity, uint64_t* record_off) {
+    if (c && c->n_cleaned) return c->fail(E_STATE, "elp_fetch_bam: elp_clean_sam rewrote %llu CIGARs; the stored records still carry the old ones (use elp_fetch)", (unsigned long long)c->n_cleaned);
     if (!c || (!out && n)) return ELP_EINVAL;
     cudaSetDevice(c->device);
     if (n == 0) { if (record_off) record_off[0] = 0; return ELP_OK; }
@@ -350,9 +436,29 @@ extern "C" int elp_fetch_bam(elp_ctx* c, uint64_t first, uint64_t n, uint8_t* ou
     return ELP_OK;
 }
 
+extern "C" int elp_set_target_regions(elp_ctx* c, int32_t contig, const int32_t* se, uint64_t n_intervals, int already_flat) {
+    if (!c) return ELP_EINVAL;
+    cudaSetDevice(c->device);
+    if (contig < 0 || contig >= c->n_contigs) return c->fail(E_INVAL, "elp_set_target_regions: contig %d out of range", contig);
+    if ((int)c->d_regions.size() != c->n_contigs) { c->d_regions.assign(c->n_contigs, nullptr); c->n_regions.assign(c->n_contigs, 0); }
+    std::vector<std::pair<int32_t, int32_t>> iv(n_intervals);
+    for (uint64_t i = 0; i < n_intervals; i++) iv[i] = {se[2 * i], se[2 * i + 1]};
+    uint64_t n = n_intervals;
+    if (!already_flat && n > 1) {   // intervals.ParallelSortByStart + ParallelFlatten (intervals/intervals.go:88-117)
+        std::stable_sort(iv.begin(), iv.end(), [](const std::pair<int32_t, int32_t>& a, const std::pair<int32_t, int32_t>& b) { return a.first < b.first; });
+        uint64_t m = 0;
+        for (uint64_t i = 0; i < n; i++) { if (m > 0 && iv[i].first <= iv[m - 1].second) { if (iv[i].second > iv[m - 1].second) iv[m - 1].second = iv[i].second; } else iv[m++] = iv[i]; }
+        n = m;
+    }
+    if (c->d_regions[contig]) { cudaFree(c->d_regions[contig]); c->d_regions[contig] = nullptr; }
+    if (n) { CUDA_TRY(c, cudaMalloc(&c->d_regions[contig], n * 8)); CUDA_TRY(c, cudaMemcpy(c->d_regions[contig], iv.data(), n * 8, cudaMemcpyHostToDevice)); }
+    c->n_regions[contig] = n; c->regions_dirty = true;
+    return ELP_OK;
+}
+
 extern "C" int elp_set_ingest_filter(elp_ctx* c, uint32_t mask, int32_t min_mapq) {
     if (!c) return ELP_EINVAL;
-    if (mask & ~(uint32_t)(ELP_FILTER_UNMAPPED | ELP_FILTER_UNMAPPED_STRICT | ELP_FILTER_NON_EXACT | ELP_FILTER_DUPLICATES)) return c->fail(E_INVAL, "elp_set_ingest_filter: unknown filter bits 0x%x", mask);
+    if (mask & ~(uint32_t)(ELP_FILTER_UNMAPPED | ELP_FILTER_UNMAPPED_STRICT | ELP_FILTER_NON_EXACT | ELP_FILTER_DUPLICATES | ELP_FILTER_NON_EXACT_STRICT | ELP_FILTER_TARGET_REGIONS)) return c->fail(E_INVAL, "elp_set_ingest_filter: unknown filter bits 0x%x", mask);
     c->filter_mask = mask; c->filter_min_mapq = min_mapq;
     return ELP_OK;
 }

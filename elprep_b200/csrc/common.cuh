@@ -38,6 +38,7 @@
 #define DERR_BAM 0x400u          // malformed BAM record (lengths / optional fields do not add up)
 #define DERR_BAM_RG 0x800u       // RG:Z value that is not an @RG ID of the header
 #define DERR_BAM_CG 0x1000u      // CG:B long-CIGAR convention
+#define DERR_CLEANSAM 0x4000u    // "Unexpected non-0 relative clipping position in CleanSam." (filters/utils.go:96)
 #define DERR_SPREAD_NAME 0x2000u // QNAME longer than a spread record holds (comm.cu)
 
 // FLAG bits (sam/sam-types.go:485-520)

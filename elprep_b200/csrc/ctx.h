@@ -105,6 +105,8 @@ struct elp_ctx {
     DBuf<uint8_t> bam_all; DBuf<uint64_t> bam_all_off; uint64_t n_bam = 0, bam_reads = 0;   // all raw records (for elp_fetch_bam) and the start of every read's record
     DBuf<uint64_t> bam_start;                 // starts of the records that pass the ingest filters
     uint32_t filter_mask = 0; int32_t filter_min_mapq = 0; uint64_t n_filtered = 0;   // elp_set_ingest_filter
+    std::vector<int32_t*> d_regions; std::vector<uint64_t> n_regions; const int32_t** d_region_ptrs = nullptr; uint64_t* d_n_regions = nullptr; bool regions_dirty = true;   // target regions (BED) of RemoveNonOverlappingReads
+    uint64_t n_cleaned = 0;                  // reads whose CIGAR elp_clean_sam rewrote
     uint8_t* d_rg_names = nullptr; uint32_t* d_rg_name_off = nullptr; std::vector<std::string> rg_ids;   // @RG IDs for the RG:Z match
     DBuf<int32_t> lseq_stage;       // staging for l_seq of the batch being appended
     DBuf<uint64_t> off_stage;       // staging for batch-relative offsets

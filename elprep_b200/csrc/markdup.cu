@@ -410,6 +410,7 @@ int check_device_errors(elp_ctx* c) {
     if (e & DERR_BAM_RG) return c->fail(E_BAM, "BAM record with an RG:Z value that is not an @RG ID of the header");
     if (e & DERR_BAM) return c->fail(E_BAM, "malformed BAM alignment record (field lengths and block_size do not add up)");
     if (e & DERR_READLEN_LIMIT) return c->fail(E_LIMIT, "BQSR: read longer than the device kernel supports");
+    if (e & DERR_CLEANSAM) return c->fail(E_LIMIT, "Unexpected non-0 relative clipping position in CleanSam.");
     if (e & DERR_SPREAD_NAME) return c->fail(E_LIMIT, "cross-group pair exchange: QNAME longer than 92 bytes");
     return c->fail(E_CUDA, "unknown device error word 0x%x", e);
 }

@@ -115,6 +115,23 @@ class Context:
     def set_ingest_filter(self, mask=0, min_mapq=0):
         self._ck(self.L.elp_set_ingest_filter(self.h, mask, min_mapq))
 
+    def set_target_regions(self, contig, start_end, already_flat=False):
+        se = np.ascontiguousarray(start_end, dtype=np.int32).reshape(-1)
+        self._ck(self.L.elp_set_target_regions(self.h, contig, _vp(se) if se.size else None, se.size // 2, int(already_flat)))
+
+    def clean_sam(self):
+        """filters.CleanSam over the reads appended so far; returns the number of rewritten CIGARs"""
+        k = C.c_uint64()
+        self._ck(self.L.elp_clean_sam(self.h, C.byref(k)))
+        return int(k.value)
+
+    def debug_cigar(self):
+        off = np.zeros(self.n + 1, np.uint64)
+        cap = 64 * max(1, self.n)
+        cg = np.zeros(cap, np.uint32)
+        self._ck(self.L.elp_debug_cigar(self.h, _vp(off), _vp(cg), cap))
+        return off, cg[:int(off[-1])]
+
     def n_filtered(self):
         return int(self.L.elp_n_filtered(self.h))
 

@@ -72,6 +72,58 @@ def RemoveNonExactMappingReads(header):
     return flt
 
 
+def RemoveNonOverlappingReads(regions):
+    """filters.RemoveNonOverlappingReads (filters/simple-filters.go:310-328) for the columnar path.  regions: per-contig (k,2) int32 arrays, the
+    Start / End of the BED records; sorted by start and flattened here (ParallelSortByStart + ParallelFlatten).  Unmapped reads and reads without
+    read bases use [POS, POS]; a contig without regions (or RNAME *) drops the read (intervals.Overlap of an empty slice)."""
+    flat = []
+    for iv in regions:
+        iv = np.asarray(iv, dtype=np.int64).reshape(-1, 2)
+        iv = iv[np.argsort(iv[:, 0], kind="stable")]
+        out = []
+        for s_, e_ in iv:
+            if out and s_ <= out[-1][1]:
+                out[-1][1] = max(out[-1][1], e_)
+            else:
+                out.append([int(s_), int(e_)])
+        flat.append(np.array(out, dtype=np.int64).reshape(-1, 2))
+
+    def overlap(iv, start, end):       # intervals.Overlap (intervals/intervals.go:146-164)
+        left, right = 0, len(iv) - 1
+        while left <= right:
+            mid = (left + right) // 2
+            if iv[mid][0] > end - 1:
+                right = mid - 1
+            elif iv[mid][1] <= start - 1:
+                left = mid + 1
+            else:
+                return True
+        return False
+
+    def make(header):
+        def flt(batch):
+            keep = np.zeros(batch.n, bool)
+            co = batch.cigar_off.astype(np.int64)
+            for i in range(batch.n):
+                pos = int(batch.pos[i]); end = pos
+                if not (int(batch.flag[i]) & 0x4):
+                    ops = batch.cigar[co[i]:co[i + 1]]
+                    rl = sum(int(o >> 4) for o in ops if int(o & 15) in (0, 1, 4, 7, 8))
+                    if rl > 0:
+                        end = pos + sum(int(o >> 4) for o in ops if int(o & 15) in (0, 2, 3, 7, 8)) - 1
+                r = int(batch.refid[i])
+                keep[i] = 0 <= r < len(flat) and overlap(flat[r], pos, end)
+            return _keep(batch, keep)
+        return flt
+    return make
+
+
+def CleanSam(header):
+    """filters.CleanSam (filters/simple-filters.go:292-306): runs on the device over everything appended (DeviceSam.AddNodes applies it after the
+    last batch); MAPQ 0 for unmapped reads, CIGAR soft-clipped at the end of the contig (softClipEndOfRead, filters/utils.go:82-119)."""
+    return _DeviceOp("clean_sam")
+
+
 def RemoveMappingQualityLessThan(mq):
     """filters.RemoveMappingQualityLessThan (simple-filters.go:332-347) -> Filter"""
     if mq == 0:
@@ -159,6 +211,8 @@ class DeviceSam:
                 b = a(b)
             self._batches.append(b)
             self.ctx.append(b)
+        if any(isinstance(a, _DeviceOp) and a.kind == "clean_sam" for a in alignment_filters):
+            self.ctx.clean_sam()
         so = device.SO_COORDINATE if sorting_order == sam.Coordinate else (_lib_const("SO_QUERYNAME") if sorting_order == sam.Queryname else device.SO_KEEP)
         opticals = any(isinstance(a, _DeviceOp) and a.kind == "markdup" and a.kw["alsoOpticals"] for a in alignment_filters)
         self.ctx.sort_markdup(so, (2 if opticals else 1) if self._markdup else 0)           # the Finalize node

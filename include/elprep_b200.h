@@ -129,9 +129,19 @@ int elp_append_bam(elp_ctx *ctx, const uint8_t *records, uint64_t n_bytes, const
 #define ELP_FILTER_UNMAPPED_STRICT 2u
 #define ELP_FILTER_NON_EXACT 4u
 #define ELP_FILTER_DUPLICATES 8u
+#define ELP_FILTER_NON_EXACT_STRICT 16u   /* RemoveNonExactMappingReadsStrict (:115-136): optional fields X0 = 1, X1 = XM = XO = XG = 0 must all be present */
+#define ELP_FILTER_TARGET_REGIONS 32u     /* RemoveNonOverlappingReads (:310-328): keep reads whose [POS, End()] overlaps a region of elp_set_target_regions */
+/* regions of one contig as (start, end) pairs, the Start / End of the BED records as the reference's bed parser stores them; sorted by
+ * start and flattened inside unless already_flat (intervals.FromBed + ParallelSortByStart + ParallelFlatten, filters/simple-filters.go:311-315) */
+int elp_set_target_regions(elp_ctx *ctx, int32_t contig, const int32_t *start_end_pairs, uint64_t n_intervals, int already_flat);
 int elp_set_ingest_filter(elp_ctx *ctx, uint32_t mask, int32_t min_mapq);
 uint64_t elp_n_filtered(const elp_ctx *ctx);
 uint64_t elp_n_reads(const elp_ctx *ctx);
+/* filters.CleanSam (filters/simple-filters.go:292-306, softClipEndOfRead filters/utils.go:82-119) over the reads appended so far (either ingest
+ * path; call before elp_sort_markdup): MAPQ of unmapped reads becomes 0; a read that runs past the end of its contig gets its CIGAR soft-clipped
+ * there.  Returns the number of rewritten CIGARs in *n_rewritten (may be NULL).  After a rewrite elp_fetch_bam is refused (the stored records
+ * still carry the old CIGAR); the columnar elp_fetch is unaffected. */
+int elp_clean_sam(elp_ctx *ctx, uint64_t *n_rewritten);
 
 /* filters.MarkDuplicates (filters/mark-duplicates.go:406-445) + By(CoordinateLess).ParallelStableSort in the
  * Finalize of (*sam.Sam).AddNodes (sam/filter-pipeline.go:113-117, sam/sam-types.go:425-473,639-641).
@@ -241,6 +251,8 @@ int elp_fetch_wait(elp_ctx *ctx);
 uint64_t elp_fetch_bam_bytes(elp_ctx *ctx, uint64_t first, uint64_t n);
 int elp_fetch_bam(elp_ctx *ctx, uint64_t first, uint64_t n, uint8_t *out, uint64_t capacity, uint64_t *record_off);
 int elp_debug_adapt(elp_ctx *ctx, int32_t *upos, int32_t *score);
+/* arrival-order CIGARs as the context holds them (after elp_clean_sam), for parity tests: cigar_off[n+1] relative to the first operation */
+int elp_debug_cigar(elp_ctx *ctx, uint64_t *cigar_off, uint32_t *cigar, uint64_t capacity);
 
 /* ---- host utilities for callers that hold BAM files in memory: BGZF blocks are independent gzip members,
  * (de)compressed here on n_threads host threads with zlib (utils/bgzf/bgzf-files.go:95-127 reader, :324-431 writer).  No context,

@@ -81,7 +81,7 @@ def gpu_pipeline(w, bqsr=True, n_batches=1, max_cycle=500, quantize_levels=0, sq
 
 
 # ---- BAM alignment records (sam/bam-files.go:300-400) for the device ingest tests ----
-def encode_bam(batch, header, rng=None, with_aux=True):
+def encode_bam(batch, header, rng=None, with_aux=True, extra_tags=None):
     """AlignmentBatch -> (uint8 record bytes, uint64 record offsets [n+1]).  Each record carries its block_size, the fixed
     fields of parseBamAlignment, NUL-terminated name, CIGAR words, SEQ nibbles, QUAL bytes and typed optional fields
     (RG:Z plus a mix of the other value types, so that the tag walk is exercised)."""
@@ -105,6 +105,8 @@ def encode_bam(batch, header, rng=None, with_aux=True):
             if k >= 3: aux += b"ASi" + struct.pack("<i", -5) + b"XSf" + struct.pack("<f", 1.5) + b"ZBBs" + struct.pack("<I", 3) + struct.pack("<3h", 1, -2, 3) + b"XAA" + b"q"
         elif int(batch.rg[i]) >= 0:
             aux += b"RGZ" + ids[int(batch.rg[i])].encode() + b"\0"
+        if extra_tags is not None:
+            aux += extra_tags[i]
         body = struct.pack("<iiBBHHHiiii", int(batch.refid[i]), int(batch.pos[i]) - 1, len(name), int(batch.mapq[i]), 4680, (co[i + 1] - co[i]) & 0xffff,
                            int(batch.flag[i]), L, int(batch.nref[i]), int(batch.pnext[i]) - 1, int(batch.tlen[i])) + name + cig + seq + qual + aux
         out += struct.pack("<I", len(body)) + body
