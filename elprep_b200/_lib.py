@@ -24,7 +24,7 @@ class ElpConfig(C.Structure):
 
 class ElpBatch(C.Structure):
     _fields_ = [("n", C.c_uint64)] + [(k, C.c_void_p) for k in
-                ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "l_seq", "seq", "qual")]
+                ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "l_seq", "seq", "qual", "opt_flags")]
 
 
 class ElpDupMetrics(C.Structure):
@@ -39,7 +39,7 @@ class ElpKernelStat(C.Structure):
 
 
 EXPORTS = ["elp_create", "elp_destroy", "elp_last_error", "elp_reserve", "elp_reset", "elp_set_reference", "elp_set_known_sites",
-           "elp_set_target_regions", "elp_clean_sam", "elp_debug_cigar", "elp_comm_unique_id", "elp_comm_init", "elp_comm_set_partition", "elp_comm_destroy", "elp_bqsr_tables_allreduce", "elp_optical_allreduce", "elp_bqsr_tables_clear", "elp_bqsr_tables_write_elrecal", "elp_bqsr_tables_add_elrecal", "elp_optical_write_gob", "elp_optical_add_gob", "elp_append_batch", "elp_append_batch_async", "elp_append_wait", "elp_fetch_async", "elp_fetch_wait", "elp_append_bam", "elp_set_ingest_filter", "elp_n_filtered", "elp_n_reads", "elp_sort_markdup", "elp_bqsr_gather", "elp_bqsr_tables_len", "elp_bqsr_n_cov",
+           "elp_fetch_opt_flags", "elp_set_target_regions", "elp_clean_sam", "elp_debug_cigar", "elp_comm_unique_id", "elp_comm_init", "elp_comm_set_partition", "elp_comm_destroy", "elp_bqsr_tables_allreduce", "elp_optical_allreduce", "elp_bqsr_tables_clear", "elp_bqsr_tables_write_elrecal", "elp_bqsr_tables_add_elrecal", "elp_optical_write_gob", "elp_optical_add_gob", "elp_append_batch", "elp_append_batch_async", "elp_append_wait", "elp_fetch_async", "elp_fetch_wait", "elp_append_bam", "elp_set_ingest_filter", "elp_n_filtered", "elp_n_reads", "elp_sort_markdup", "elp_bqsr_gather", "elp_bqsr_tables_len", "elp_bqsr_n_cov",
            "elp_bqsr_cov_name", "elp_bqsr_tables_get", "elp_bqsr_tables_put", "elp_bqsr_tables_device", "elp_bqsr_finalize",
            "elp_bqsr_empirical_get", "elp_bqsr_apply", "elp_fetch", "elp_fetch_qual_bytes", "elp_fetch_bam", "elp_fetch_bam_bytes", "elp_debug_adapt", "elp_launch_count",
            "elp_kernel_stats", "elp_synchronize", "elp_reset_stats", "elp_timer_start", "elp_timer_stop", "elp_debug_sort_u64", "elp_debug_sort_u128",
@@ -83,6 +83,7 @@ def load():
     for f in ("elp_bqsr_tables_write_elrecal", "elp_bqsr_tables_add_elrecal", "elp_optical_write_gob", "elp_optical_add_gob"):
         getattr(L, f).argtypes = [C.c_void_p, C.c_char_p]
     L.elp_bqsr_tables_clear.argtypes = [C.c_void_p]
+    L.elp_fetch_opt_flags.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]
     L.elp_set_target_regions.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_int]
     L.elp_clean_sam.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.elp_debug_cigar.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]

@@ -27,7 +27,7 @@ struct BamArgs {
     uint64_t n, n0;                       // records in this call, reads already in the context
     const uint8_t* raw; const uint64_t* start; uint64_t n_bytes;   // start[i]: offset of record i's block_size field
     int chained;                          // start[] has n + 1 entries and start[i + 1] must be the end of record i (no filter ran)
-    int32_t *refid, *pos, *nref, *pnext, *tlen, *rg; uint16_t* flag; uint8_t* mapq;
+    int32_t *refid, *pos, *nref, *pnext, *tlen, *rg; uint16_t* flag; uint8_t* mapq; uint8_t* optf;
     uint32_t *len_qname, *len_cigar, *len_seq, *len_qual;   // [n] lengths, scanned afterwards
     const uint8_t* rg_names; const uint32_t* rg_name_off; int n_rg; int n_contigs;
     uint32_t* err;
@@ -54,13 +54,14 @@ __global__ void __launch_bounds__(256) bam_fixed_kernel(BamArgs A) {
     const uint64_t k = A.n0 + i;
     A.refid[k] = refid < 0 ? -1 : refid; A.pos[k] = pos + 1; A.flag[k] = (uint16_t)flag; A.mapq[k] = (uint8_t)mapq;
     A.nref[k] = nref < 0 ? -1 : nref; A.pnext[k] = pnext + 1; A.tlen[k] = tlen;
-    int32_t rg = -1;
+    int32_t rg = -1; uint8_t optf = 0;
     if (!bad) {
         // optional fields: tag[2] type[1] value (sam/bam-files.go:369-397)
         uint64_t x = BAM_FIXED + var;
         while (x + 3 <= rec_len) {
             const uint8_t t0 = r[x], t1 = r[x + 1], ty = r[x + 2];
             x += 3;
+            if (t0 == 's' && t1 == 'r') optf |= 1;          // the sr tag of `elprep split` (sam/split-merge.go:286-293)
             uint64_t sz = 0; bool str = false;
             switch (ty) {
                 case 'A': case 'c': case 'C': sz = 1; break;
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) bam_fixed_kernel(BamArgs A) {
     }
     if (rg == -2) { atomicOr(A.err, DERR_BAM_RG); rg = -1; }
     if (bad) atomicOr(A.err, bad == 2 ? DERR_BAM_CG : DERR_BAM);
-    A.rg[k] = rg;
+    A.rg[k] = rg; A.optf[k] = optf;
     A.len_qname[i] = bad ? 0 : l_name - 1; A.len_cigar[i] = bad ? 0 : n_cig;
     A.len_seq[i] = bad ? 0 : (uint32_t)((l_seq + 1) >> 1); A.len_qual[i] = bad ? 0 : (uint32_t)l_seq;
 }
@@ -347,12 +348,12 @@ extern "C" int elp_append_bam(elp_ctx* c, const uint8_t* records, uint64_t n_byt
         CUDA_TRY(c, cudaMemcpy(c->d_rg_name_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
     }
     TRY(grow(c, c->refid, n1 + 1, n0)); TRY(grow(c, c->pos, n1 + 1, n0)); TRY(grow(c, c->nref, n1 + 1, n0)); TRY(grow(c, c->pnext, n1 + 1, n0)); TRY(grow(c, c->tlen, n1 + 1, n0));
-    TRY(grow(c, c->rg, n1 + 1, n0)); TRY(grow(c, c->flag, n1 + 2, n0)); TRY(grow(c, c->mapq, n1 + 1, n0));
+    TRY(grow(c, c->rg, n1 + 1, n0)); TRY(grow(c, c->flag, n1 + 2, n0)); TRY(grow(c, c->mapq, n1 + 1, n0)); TRY(grow(c, c->optf, n1 + 1, n0));
     TRY(grow(c, c->qname_off, n1 + 2, n0 + 1)); TRY(grow(c, c->cigar_off, n1 + 2, n0 + 1)); TRY(grow(c, c->qual_off, n1 + 2, n0 + 1)); TRY(grow(c, c->seq_off, n1 + 2, n0 + 1));
     TRY(grow(c, c->scan_tmp, 4 * (bn + 4) + 8, 0));   // (the keep flags above are dead by now)
     BamArgs A{};
     A.n = bn; A.n0 = n0; A.raw = c->bam_raw.p; A.start = d_start; A.n_bytes = n_bytes; A.chained = d_start == c->bam_off.p;
-    A.refid = c->refid.p; A.pos = c->pos.p; A.nref = c->nref.p; A.pnext = c->pnext.p; A.tlen = c->tlen.p; A.rg = c->rg.p; A.flag = c->flag.p; A.mapq = c->mapq.p;
+    A.refid = c->refid.p; A.pos = c->pos.p; A.nref = c->nref.p; A.pnext = c->pnext.p; A.tlen = c->tlen.p; A.rg = c->rg.p; A.flag = c->flag.p; A.mapq = c->mapq.p; A.optf = c->optf.p;
     A.len_qname = c->scan_tmp.p; A.len_cigar = c->scan_tmp.p + (bn + 4); A.len_seq = c->scan_tmp.p + 2 * (bn + 4); A.len_qual = c->scan_tmp.p + 3 * (bn + 4);
     A.rg_names = c->d_rg_names; A.rg_name_off = c->d_rg_name_off; A.n_rg = c->n_rg; A.n_contigs = c->n_contigs; A.err = c->d_err;
     c->begin("bam_fixed", (double)bn * 36 + (double)n_bytes * 0.2);

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) bqsr_prep2_kernel(GatherArgs A, Prep2Args
         const uint8_t mq = A.mapq[k];
         const int32_t refid = A.refid[k], pos0 = A.pos[k], g = A.rg[k], L0 = A.lseq[k];
         const int nc0 = (int)A.ncigar[k];
-        bool elig = (mq > 0 && mq < 255) && !(f & (F_SECONDARY | F_DUPLICATE | F_QCFAILED)) && !((f & F_UNMAPPED) || refid < 0 || pos0 == 0) && pos0 > 0 && L0 > 0 &&
+        bool elig = !(A.optf[k] & 1u) && (mq > 0 && mq < 255) && !(f & (F_SECONDARY | F_DUPLICATE | F_QCFAILED)) && !((f & F_UNMAPPED) || refid < 0 || pos0 == 0) && pos0 > 0 && L0 > 0 &&
                     g >= 0 && g < A.n_rg && refid < A.n_contigs;
         if (elig && pos0 > A.contig_len[refid]) elig = false;
         if (elig) {

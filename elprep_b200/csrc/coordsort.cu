@@ -140,6 +140,7 @@ struct GatherCols {
     const uint64_t *qual_off, *seq_off, *cigar_off;
     int32_t *s_refid, *s_pos, *s_nref, *s_pnext, *s_tlen, *s_rg, *s_lseq; uint16_t* s_flag; uint8_t* s_mapq;
     uint64_t *s_qual_off, *s_seq_off, *s_cigar_off; uint32_t* s_ncigar;
+    const uint8_t* optf; uint8_t* s_optf;
 };
 
 // The fixed-width columns of a read packed into one 64-byte row (streaming pass, coalesced), so that the permuted gather below
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(uint64_t n, GatherCols g
     r[0] = make_uint4((uint32_t)g.refid[i], (uint32_t)g.pos[i], (uint32_t)g.nref[i], (uint32_t)g.pnext[i]);
     r[1] = make_uint4((uint32_t)g.tlen[i], (uint32_t)g.rg[i], (uint32_t)(q1 - q0), (uint32_t)(c1 - c0));
     r[2] = make_uint4((uint32_t)q0, (uint32_t)(q0 >> 32), (uint32_t)s0, (uint32_t)(s0 >> 32));
-    r[3] = make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)g.mapq[i], 0u);
+    r[3] = make_uint4((uint32_t)c0, (uint32_t)(c0 >> 32), (uint32_t)g.mapq[i], (uint32_t)g.optf[i]);
 }
 
 __global__ void __launch_bounds__(256) gather_cols_kernel(uint64_t n, const uint32_t* __restrict__ perm, GatherCols g, const uint4* __restrict__ rows) {
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) gather_cols_kernel(uint64_t n, const uint
     const uint4 a = __ldg(r), b = __ldg(r + 1), c = __ldg(r + 2), d = __ldg(r + 3);
     g.s_refid[k] = (int32_t)a.x; g.s_pos[k] = (int32_t)a.y; g.s_nref[k] = (int32_t)a.z; g.s_pnext[k] = (int32_t)a.w; g.s_tlen[k] = (int32_t)b.x; g.s_rg[k] = (int32_t)b.y;
     g.s_flag[k] = g.flag[i];                       // FLAG from the column: duplicate marking set bits after the rows were packed
-    g.s_mapq[k] = (uint8_t)d.z;
+    g.s_mapq[k] = (uint8_t)d.z; g.s_optf[k] = (uint8_t)d.w;
     g.s_qual_off[k] = ((uint64_t)c.y << 32) | c.x; g.s_lseq[k] = (int32_t)b.z; g.s_seq_off[k] = ((uint64_t)c.w << 32) | c.z;
     g.s_cigar_off[k] = ((uint64_t)d.y << 32) | d.x; g.s_ncigar[k] = b.w;
 }
@@ -271,13 +272,13 @@ int phase_coordinate_sort(elp_ctx* c, int order) {   // 0 keep, 1 coordinate, 2 
     // gather the fixed-width columns into output order
     CUDA_TRY(c, c->s_refid.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_pos.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_nref.reserve(n + 4, c->stream));
     CUDA_TRY(c, c->s_pnext.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_tlen.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_rg.reserve(n + 4, c->stream));
-    CUDA_TRY(c, c->s_lseq.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_flag.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_mapq.reserve(n + 4, c->stream));
+    CUDA_TRY(c, c->s_lseq.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_flag.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_mapq.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_optf.reserve(n + 4, c->stream));
     CUDA_TRY(c, c->s_qual_off.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_seq_off.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_cigar_off.reserve(n + 4, c->stream));
     CUDA_TRY(c, c->s_ncigar.reserve(n + 4, c->stream)); CUDA_TRY(c, c->s_out_off.reserve(n + 4, c->stream));
     if (n) {
         GatherCols g{c->refid.p, c->pos.p, c->nref.p, c->pnext.p, c->tlen.p, c->rg.p, c->flag.p, c->mapq.p, c->qual_off.p, c->seq_off.p, c->cigar_off.p,
                      c->s_refid.p, c->s_pos.p, c->s_nref.p, c->s_pnext.p, c->s_tlen.p, c->s_rg.p, c->s_lseq.p, c->s_flag.p, c->s_mapq.p,
-                     c->s_qual_off.p, c->s_seq_off.p, c->s_cigar_off.p, c->s_ncigar.p};
+                     c->s_qual_off.p, c->s_seq_off.p, c->s_cigar_off.p, c->s_ncigar.p, c->optf.p, c->s_optf.p};
         // rows live in the key scratch (free here): 4 x uint4 per read
         CUDA_TRY(c, c->keys_a.reserve(8 * n + 8, c->stream));
         uint4* rows = reinterpret_cast<uint4*>(c->keys_a.p);

@@ -98,6 +98,7 @@ struct elp_ctx {
     DBuf<int32_t> refid, pos, nref, pnext, tlen, rg;
     DBuf<uint16_t> flag;
     DBuf<uint8_t> mapq;
+    DBuf<uint8_t> optf;                       // elp_batch.opt_flags (ELP_OPT_SR ...)
     DBuf<uint64_t> qname_off, cigar_off, qual_off, seq_off;   // [n+1]
     DBuf<uint8_t> qname, seq, qual;
     DBuf<uint32_t> cigar;
@@ -135,7 +136,7 @@ struct elp_ctx {
     DBuf<uint32_t> perm;                      // [n] arrival index of k-th output record
     DBuf<int32_t> s_refid, s_pos, s_nref, s_pnext, s_tlen, s_rg, s_lseq;
     DBuf<uint16_t> s_flag;
-    DBuf<uint8_t> s_mapq;
+    DBuf<uint8_t> s_mapq, s_optf;
     DBuf<uint64_t> s_qual_off, s_seq_off, s_cigar_off, s_out_off;   // s_out_off[n+1]: offsets of the output qual stream
     DBuf<uint32_t> s_ncigar;
     DBuf<uint8_t> qual_out;                   // recalibrated QUAL in output order

@@ -86,7 +86,7 @@ class Context:
     def append(self, batch):
         b = _lib.ElpBatch()
         b.n = batch.n
-        for k in ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "seq", "qual"):
+        for k in ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "seq", "qual", "opt_flags"):
             setattr(b, k, _vp(getattr(batch, k)))
         b.l_seq = _vp(batch.lseq)
         self._ck(self.L.elp_append_batch(self.h, C.byref(b)))
@@ -95,7 +95,7 @@ class Context:
         """queue the upload and return; ``batch`` (page-locked) must stay alive and unchanged until append_wait()"""
         b = _lib.ElpBatch()
         b.n = batch.n
-        for k in ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "seq", "qual"):
+        for k in ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg", "qname_off", "qname", "cigar_off", "cigar", "seq", "qual", "opt_flags"):
             setattr(b, k, _vp(getattr(batch, k)))
         b.l_seq = _vp(batch.lseq)
         self._ck(self.L.elp_append_batch_async(self.h, C.byref(b)))
@@ -124,6 +124,12 @@ class Context:
         k = C.c_uint64()
         self._ck(self.L.elp_clean_sam(self.h, C.byref(k)))
         return int(k.value)
+
+    def fetch_opt_flags(self, first=0, n=None):
+        n = self.n - first if n is None else n
+        out = np.zeros(n, np.uint8)
+        self._ck(self.L.elp_fetch_opt_flags(self.h, first, n, _vp(out)))
+        return out
 
     def debug_cigar(self):
         off = np.zeros(self.n + 1, np.uint64)

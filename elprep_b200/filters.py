@@ -72,6 +72,15 @@ def RemoveNonExactMappingReads(header):
     return flt
 
 
+def RemoveOptionalReads(header):
+    """filters.RemoveOptionalReads (filters/simple-filters.go:142-150): drops the reads that carry the `sr` tag (opt_flags bit 0) -- the copies
+    `elprep split` leaves in a group file for reads whose mate lies in another group; a no-op unless the header has the @sr user record"""
+    if "@sr" not in getattr(header, "UserRecords", {}):
+        return None
+    header.UserRecords.pop("@sr")
+    return lambda b: _keep(b, (b.opt_flags & 1) == 0)
+
+
 def RemoveNonOverlappingReads(regions):
     """filters.RemoveNonOverlappingReads (filters/simple-filters.go:310-328) for the columnar path.  regions: per-contig (k,2) int32 arrays, the
     Start / End of the BED records; sorted by start and flattened here (ParallelSortByStart + ParallelFlatten).  Unmapped reads and reads without

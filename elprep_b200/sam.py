@@ -126,7 +126,7 @@ class AlignmentBatch:
     """Columnar batch of alignment records (the ``elp_batch`` payload)."""
 
     FIELDS = ("refid", "pos", "flag", "mapq", "nref", "pnext", "tlen", "rg",
-              "qname_off", "qname", "cigar_off", "cigar", "lseq", "seq", "qual")
+              "qname_off", "qname", "cigar_off", "cigar", "lseq", "seq", "qual", "opt_flags")
 
     def __init__(self, **kw):
         self.refid = np.ascontiguousarray(kw["refid"], dtype=np.int32)
@@ -145,6 +145,8 @@ class AlignmentBatch:
         self.lseq = np.ascontiguousarray(kw["lseq"], dtype=np.int32)
         self.seq = np.ascontiguousarray(kw["seq"], dtype=np.uint8)
         self.qual = np.ascontiguousarray(kw["qual"], dtype=np.uint8)
+        # presence bits of optional fields the path looks at (bit 0: the `sr` tag of `elprep split`, sam/split-merge.go:286-293)
+        self.opt_flags = np.ascontiguousarray(kw["opt_flags"], dtype=np.uint8) if kw.get("opt_flags") is not None else np.zeros(n, dtype=np.uint8)
         assert self.qname_off.shape[0] == n + 1 and self.cigar_off.shape[0] == n + 1
         self._seq_off = None
         self._qual_off = None
@@ -196,7 +198,7 @@ class AlignmentBatch:
         _, ql = ragged(self.qual_off, self.qual)
         return AlignmentBatch(refid=self.refid[idx], pos=self.pos[idx], flag=self.flag[idx], mapq=self.mapq[idx],
                               nref=self.nref[idx], pnext=self.pnext[idx], tlen=self.tlen[idx], rg=self.rg[idx],
-                              qname_off=qo, qname=qn, cigar_off=co, cigar=cg, lseq=self.lseq[idx], seq=sq, qual=ql)
+                              qname_off=qo, qname=qn, cigar_off=co, cigar=cg, lseq=self.lseq[idx], seq=sq, qual=ql, opt_flags=self.opt_flags[idx])
 
     @staticmethod
     def concat(batches):

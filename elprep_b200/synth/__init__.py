@@ -159,4 +159,4 @@ def take(batch, idx, threads=None):
     _, ql = ragged(batch.qual_off, batch.qual)
     return sam.AlignmentBatch(refid=batch.refid[idx], pos=batch.pos[idx], flag=batch.flag[idx], mapq=batch.mapq[idx], nref=batch.nref[idx],
                               pnext=batch.pnext[idx], tlen=batch.tlen[idx], rg=batch.rg[idx], qname_off=qo, qname=qn, cigar_off=co, cigar=cg,
-                              lseq=batch.lseq[idx], seq=sq, qual=ql)
+                              lseq=batch.lseq[idx], seq=sq, qual=ql, opt_flags=batch.opt_flags[idx])

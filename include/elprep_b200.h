@@ -81,7 +81,12 @@ typedef struct {
     const uint64_t *qname_off; const uint8_t *qname;   /* qname_off[n+1], bytes without NUL */
     const uint64_t *cigar_off; const uint32_t *cigar;  /* cigar_off[n+1] */
     const int32_t *l_seq; const uint8_t *seq; const uint8_t *qual;
+    const uint8_t *opt_flags;   /* may be NULL. Per read, presence bits of optional fields the path looks at: ELP_OPT_SR = the read carries the `sr`
+                                 * tag `elprep split` puts on the group-file copy of a read whose mate lies in another group (sam/split-merge.go:286-293):
+                                 * such a read is never recalibrated (recalibrateAln, filters/bqsr.go:225-229) and RemoveOptionalReads drops it at the end
+                                 * (filters/simple-filters.go:142-150).  elp_append_bam sets the bit from the record's optional fields. */
 } elp_batch;
+#define ELP_OPT_SR 1u
 
 /* per-kernel device timing (CUDA events on the launching stream), for bench.py's roofline object */
 typedef struct {
@@ -251,6 +256,8 @@ int elp_fetch_wait(elp_ctx *ctx);
 uint64_t elp_fetch_bam_bytes(elp_ctx *ctx, uint64_t first, uint64_t n);
 int elp_fetch_bam(elp_ctx *ctx, uint64_t first, uint64_t n, uint8_t *out, uint64_t capacity, uint64_t *record_off);
 int elp_debug_adapt(elp_ctx *ctx, int32_t *upos, int32_t *score);
+/* opt_flags of output records [first, first+n) (what filters.RemoveOptionalReads looks at when the worker writes its output) */
+int elp_fetch_opt_flags(elp_ctx *ctx, uint64_t first, uint64_t n, uint8_t *opt_flags);
 /* arrival-order CIGARs as the context holds them (after elp_clean_sam), for parity tests: cigar_off[n+1] relative to the first operation */
 int elp_debug_cigar(elp_ctx *ctx, uint64_t *cigar_off, uint32_t *cigar, uint64_t capacity);
 

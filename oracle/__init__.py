@@ -30,7 +30,7 @@ class _Reads(C.Structure):
     _fields_ = [("n", C.c_int64), ("refid", C.c_void_p), ("pos", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p),
                 ("nref", C.c_void_p), ("pnext", C.c_void_p), ("tlen", C.c_void_p), ("rg", C.c_void_p),
                 ("qname_off", C.c_void_p), ("qname", C.c_void_p), ("cigar_off", C.c_void_p), ("cigar", C.c_void_p),
-                ("lseq", C.c_void_p), ("seq_off", C.c_void_p), ("seq", C.c_void_p), ("qual_off", C.c_void_p), ("qual", C.c_void_p)]
+                ("lseq", C.c_void_p), ("seq_off", C.c_void_p), ("seq", C.c_void_p), ("qual_off", C.c_void_p), ("qual", C.c_void_p), ("opt_flags", C.c_void_p)]
 
 
 class _Header(C.Structure):
@@ -82,6 +82,7 @@ class OracleReads:
             setattr(s, k, _p(getattr(batch, k)))
         s.seq_off = _p(batch.seq_off)
         s.qual_off = _p(batch.qual_off)
+        s.opt_flags = _p(batch.opt_flags)
         self.s = s
 
 

@@ -960,6 +960,7 @@ static void prepare_cycle(uint16_t flag, int seqlen, int *cycleFactor, int *incr
 
 /* ---------------------------------------------- bqsr.go:225-244 recalibrateAln */
 static int recalibrate_aln(const orc_reads *r, const orc_header *h, int64_t i, const waln *a) {
+    if (r->opt_flags && (r->opt_flags[i] & 1)) return 0;   /* _, found := aln.TAGS.Get(sr); if found { return false } (bqsr.go:226-229) */
     if (!(r->mapq[i] > 0 && r->mapq[i] < 255)) return 0;
     if (a->flag & (0x100 | 0x400 | 0x200)) return 0;
     if (is_strict_unmapped(a)) return 0;

@@ -38,6 +38,7 @@ typedef struct {
     const int32_t *lseq;
     const uint64_t *seq_off;  const uint8_t *seq;
     const uint64_t *qual_off; uint8_t *qual; /* mutated by apply */
+    const uint8_t *opt_flags; /* may be NULL; bit 0: the read carries the sr tag (sam/split-merge.go:286-293) */
 } orc_reads;
 
 typedef struct {
