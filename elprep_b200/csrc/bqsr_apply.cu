@@ -276,7 +276,8 @@ __global__ void __launch_bounds__(AP2_WARPS * 32, 2) bqsr_apply2_kernel(Apply2Ar
             const unsigned gb = __ballot_sync(FULL_MASK, G != 0) & gmask;
             const int lo_lane = gb ? __ffs((int)gb) - 1 : (int)lane, hi_lane = gb ? 31 - __clz((int)gb) : (int)lane;
             const int lf = G ? i0 + (__ffs((int)G) - 1) : 0x7fffffff, ll = G ? i0 + (31 - __clz((int)G)) : -1;
-            const int leftPos = gb ? __shfl_sync(FULL_MASK, lf, lo_lane) : 0x7fffffff, rightPos = gb ? __shfl_sync(FULL_MASK, ll, hi_lane) : -1;
+            const int lf_x = __shfl_sync(FULL_MASK, lf, lo_lane), ll_x = __shfl_sync(FULL_MASK, ll, hi_lane);    // (every lane takes part: groups without a set bit differ)
+            const int leftPos = gb ? lf_x : 0x7fffffff, rightPos = gb ? ll_x : -1;
             // bases outside [leftPos, rightPos] read as N
 #pragma unroll
             for (int w = 0; w < 4; w++) {
