@@ -22,6 +22,9 @@ import sys
 import threading
 import time
 
+# NCCL's own banner (printed when the box sets NCCL_DEBUG) must not land on stdout, which carries exactly one JSON line
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -280,37 +283,48 @@ def main():
         dev_ms.append(a); in_ms.append(b); out_ms.append(c_); coll_ms.append(d_)
     launches = ctx.launch_count()
     stats = ctx.kernel_stats()
-    # ---- e2e: the same K steps through the public API with host buffers, software-pipelined over two contexts: while context A's
-    # batch uploads, context B (previous step) runs its device phases and downloads.  Every step still moves its full input and output.
-    ctx2 = make_ctx()
-    cs = (ctx, ctx2)
+    # ---- e2e: the same K steps through the public API with host buffers, software-pipelined over a ring of three contexts: while the
+    # batch of step s uploads into one context, the context of step s-1 runs its device phases and starts its download, and the download of
+    # step s-2 drains into the other of two page-locked output buffers.  The host->device copy engine -- the longest stage -- never waits.
+    # Every step still moves its full input and its full output.
+    ctx2, ctx3 = make_ctx(), make_ctx()
+    cs = (ctx, ctx2, ctx3)
+    out_b = tuple(torch.empty(s_, dtype=dt, pin_memory=True) for s_, dt in ((n_reads, torch.int32), (n_reads, torch.int16), (n_reads + 1, torch.int64), (int(hb.qual.size), torch.uint8)))
+    outs = (out_np, (out_b[0].numpy().view(np.uint32), out_b[1].numpy().view(np.uint16), out_b[2].numpy().view(np.uint64), out_b[3].numpy()))
 
     trace = {}
+    marks = []
 
     def timed(name, fn):
         t0 = time.perf_counter(); fn(); trace[name] = trace.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
 
     def e2e_run(k_steps):
-        for s in range(k_steps + 1):
-            cur = cs[s % 2] if s < k_steps else None
-            prev = cs[(s - 1) % 2] if s >= 1 else None
+        for s in range(k_steps + 2):
+            cur = cs[s % 3] if s < k_steps else None
+            prev = cs[(s - 1) % 3] if 1 <= s <= k_steps else None
+            prev2 = cs[(s - 2) % 3] if s >= 2 else None
             if cur is not None:
                 timed("reset+append_async", lambda: (cur.reset(), cur.append_async(hb)))
             if prev is not None:
-                timed("phases", lambda: phases(prev)); timed("fetch_async", lambda: prev.fetch_async(out_np))
+                timed("phases", lambda: phases(prev)); timed("fetch_async", lambda: prev.fetch_async(outs[(s - 1) % 2]))
+            if prev2 is not None:
+                timed("fetch_wait", prev2.fetch_wait)
             if cur is not None:
                 timed("append_wait", cur.append_wait)
-            if prev is not None:
-                timed("fetch_wait", prev.fetch_wait)
-    e2e_run(2)                                   # warm-up (allocations of the second context)
-    trace.clear()
-    barrier(ctx); ctx2.synchronize()
+            marks.append(time.perf_counter())
+    e2e_run(3)                                   # warm-up (allocations of the second and third context)
+    trace.clear(); marks.clear()
+    barrier(ctx); ctx2.synchronize(); ctx3.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     e2e_run(args.steps)
-    ctx.synchronize(); ctx2.synchronize(); torch.cuda.synchronize()
+    ctx.synchronize(); ctx2.synchronize(); ctx3.synchronize(); torch.cuda.synchronize()
     ev1.record(); ev1.synchronize()
     e2e_ms_total = ev0.elapsed_time(ev1)
+    mid = np.diff(np.array(marks[:args.steps]))                    # iterations that both upload and run phases
+    steady_ms = float(np.median(mid[1:]) * 1e3) if mid.size >= 2 else None
+    free_b, total_b = torch.cuda.mem_get_info(local)
+    hbm_used_gb = (total_b - free_b) / 1e9                 # three contexts resident
     clocks = sampler.stop() if rank == 0 else None
     tot = torch.tensor([float(np.sum(dev_ms)), float(e2e_ms_total)], device=f"cuda:{local}", dtype=torch.float64)
     cnt = torch.tensor([float(n_reads)], device=f"cuda:{local}", dtype=torch.float64)
@@ -373,9 +387,10 @@ def main():
             "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
             "config": {"workload": workload_name, "cpu_arm": f"CPU arm runs a sample: the first {args.cpu_sample} reads per step", "reads_per_gpu": n_reads, "parallelism": f"contig-group x{world}; NCCL inside the C ABI: spread-pair exchange (ncclSend/Recv) in elp_sort_markdup + one ncclAllReduce of the BQSR tables", "flush": "inputs >> L2 (re-ingested every step)"},
             "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
-                    "how": "K steps through elp_append_batch_async / phases / elp_fetch_async with pinned host buffers, software-pipelined over two contexts (upload of step s overlaps phases + download of step s-1)",
+                    "how": "K steps through elp_append_batch_async / phases / elp_fetch_async with pinned host buffers, software-pipelined over a ring of three contexts and two output buffers (upload of step s overlaps the phases of step s-1 and the download of steps s-1 / s-2)",
                     "unpipelined_ms_per_step": float(np.mean(in_ms) + np.mean(dev_ms) + np.mean(out_ms)),
-                    "host_ms_per_step_in_call": {k: v / args.steps for k, v in trace.items()}},
+                    "host_ms_per_step_in_call": {k: v / args.steps for k, v in trace.items()}, "hbm_used_gb_three_contexts": hbm_used_gb,
+                    "steady_ms_per_step": steady_ms, "note": "ms_per_step = the K timed steps including pipeline fill (first upload) and drain (last phases + download); steady_ms_per_step = median host interval between consecutive steps in the middle of the run"},
             "phases_per_rank": phases_per_rank, "roofline_graded": graded,
             "gpu_launches": launches, "verified": (verified or {}).get("ok"), "verify": verified, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": kern}
     print(json.dumps(line))

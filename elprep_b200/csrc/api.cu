@@ -303,10 +303,13 @@ static uint64_t sum_lengths(const int32_t* l, uint64_t n, uint64_t* seq_bytes) {
     *seq_bytes = y; return x;
 }
 
-// Large host<->device copies go out in pieces: a copy engine serves its queue in order, so one 4 GB cudaMemcpyAsync would hold up every
-// small copy of the OTHER contexts of a pipelined caller (the few-byte read-backs and table uploads inside their phases) until it is done.
+// Large host<->device copies go out whole by default.  (A copy engine serves its queue in order, so cutting a copy into pieces that are all
+// enqueued at once does not let another context's small copies overtake it -- measured with tools/e2e_probe.py: 32 MB pieces cost 5 % of the
+// duplex upload rate and the small copies waited just the same.  The phases therefore avoid the copy engines for their small uploads
+// (upload_small), and a pipelined caller orders its downloads so that none is in flight while another context's phases read back.)
+// ELPREP_B200_COPY_CHUNK_MB > 0 restores the pieces for experiments.
 static cudaError_t copy_chunked(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s) {
-    const size_t CH = 32u << 20;
+    static const size_t CH = [] { const char* e = getenv("ELPREP_B200_COPY_CHUNK_MB"); const long v = e ? atol(e) : 0; return v <= 0 ? ~(size_t)0 : (size_t)v << 20; }();
     for (size_t o = 0; o < bytes; o += CH) {
         cudaError_t e = cudaMemcpyAsync((char*)dst + o, (const char*)src + o, std::min(CH, bytes - o), kind, s);
         if (e != cudaSuccess) return e;

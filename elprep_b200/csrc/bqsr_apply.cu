@@ -234,9 +234,8 @@ __global__ void __launch_bounds__(AP2_WARPS * 32, 2) bqsr_apply2_kernel(Apply2Ar
             V[0] = b0.x; V[1] = b0.y; V[2] = b0.z; V[3] = b0.w; V[4] = b1.x; V[5] = b1.y; V[6] = b1.z; V[7] = b1.w;
             lanes::align_nibbles32<true>(V, (uint32_t)(reinterpret_cast<uintptr_t>(sp) & 15), (uint32_t)(ni & 1), N);
         }
-        // bytes past the read end must not look like bases
-#pragma unroll
-        for (int w = 0; w < 8; w++) { const int keep = nb - 4 * w; if (keep < 4) Q[w] = keep <= 0 ? 0u : (Q[w] & (0xffffffffu >> (8 * (4 - keep)))); }
+        // (bytes past the read end are whatever follows in the arena: they index valid table rows, are never stored, and are masked where it
+        //  matters -- the tail search below and the range check in its slow path)
         const uint32_t f = fg & 0xffffu; const int g = (int)(fg >> 16) - 1;
         bool recal = A.clut != nullptr && nb > 0;
         int cov = 0;
@@ -319,12 +318,17 @@ __global__ void __launch_bounds__(AP2_WARPS * 32, 2) bqsr_apply2_kernel(Apply2Ar
                 const uint32_t ctx = (X[j >> 3] >> (4 * (j & 7))) & 15u;
                 uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(cbase + (uint32_t)(j * stepb) + (row & 0x7fffu) + ctx));
                 R[j >> 2] = __byte_perm(R[j >> 2], v, (j & 3) == 0 ? 0x3214 : ((j & 3) == 1 ? 0x3240 : ((j & 3) == 2 ? 0x3410 : 0x4210)));
-                over |= q;
             }
-            if (over & 0x80u) errbits |= DERR_QUAL_RANGE;
-            else if (over >= 94u) {
+            // QUAL > 93 is an error (bqsr.go:968 indexes a 94-entry table): any byte >= 64 sends the lane through the exact, masked check
 #pragma unroll
-                for (int w = 0; w < 8; w++) { const uint32_t v = Q[w]; if ((((v & 0x7f7f7f7fu) + 0x22222222u) | v) & 0x80808080u) errbits |= DERR_QUAL_RANGE; }
+            for (int w = 0; w < 8; w++) over |= Q[w];
+            if (over & 0xc0c0c0c0u) {
+#pragma unroll
+                for (int w = 0; w < 8; w++) {
+                    const int keep = nb - 4 * w;
+                    const uint32_t v = keep >= 4 ? Q[w] : (keep <= 0 ? 0u : (Q[w] & (0xffffffffu >> (8 * (4 - keep)))));
+                    if ((((v & 0x7f7f7f7fu) + 0x22222222u) | v) & 0x80808080u) errbits |= DERR_QUAL_RANGE;
+                }
             }
             // bases without a context take column 16
 #pragma unroll
@@ -361,8 +365,11 @@ __global__ void __launch_bounds__(AP2_WARPS * 32, 2) bqsr_apply2_kernel(Apply2Ar
             for (uint32_t m = lane; m * 16u < end; m += 32) {
                 const uint32_t b0 = m * 16u;
                 if (b0 >= phase && b0 + 16u <= end) *reinterpret_cast<uint4*>(gbase + b0) = *reinterpret_cast<const uint4*>(img + b0);
-                else { const uint32_t lo = max(b0, phase), hi = min(b0 + 16u, end); for (uint32_t t = lo; t < hi; t++) gbase[t] = img[t]; }   // shared with a neighbouring pass
             }
+            // the first and the last 16-byte chunk may be shared with a neighbouring pass: one byte per lane (lanes 0-15 the first, 16-31 the last)
+            const uint32_t mlast = (end - 1u) >> 4;
+            if (lane < 16) { const uint32_t t = lane; if ((phase != 0 || end < 16u) && t >= phase && t < end) gbase[t] = img[t]; }
+            else { const uint32_t t = mlast * 16u + (lane - 16u); if (mlast > 0 && (end & 15u) && t < end) gbase[t] = img[t]; }
         }
         __syncwarp();
     }
