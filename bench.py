@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-sample", type=int, default=3_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-contexts", type=int, default=3, choices=(1, 3), help="contexts in the e2e pipeline ring (1: sequential, for runs where one context fills the HBM)")
     ap.add_argument("--verify", dest="verify", action="store_true", default=None, help="check the last step's output against the oracle (default: on at --gpus 1)")
     ap.add_argument("--no-verify", dest="verify", action="store_false")
     args = ap.parse_args()
@@ -287,10 +288,12 @@ def main():
     # batch of step s uploads into one context, the context of step s-1 runs its device phases and starts its download, and the download of
     # step s-2 drains into the other of two page-locked output buffers.  The host->device copy engine -- the longest stage -- never waits.
     # Every step still moves its full input and its full output.
-    ctx2, ctx3 = make_ctx(), make_ctx()
-    cs = (ctx, ctx2, ctx3)
-    out_b = tuple(torch.empty(s_, dtype=dt, pin_memory=True) for s_, dt in ((n_reads, torch.int32), (n_reads, torch.int16), (n_reads + 1, torch.int64), (int(hb.qual.size), torch.uint8)))
-    outs = (out_np, (out_b[0].numpy().view(np.uint32), out_b[1].numpy().view(np.uint16), out_b[2].numpy().view(np.uint64), out_b[3].numpy()))
+    ring = args.e2e_contexts
+    cs = (ctx,) + tuple(make_ctx() for _ in range(ring - 1))
+    outs = (out_np, out_np)
+    if ring > 1:
+        out_b = tuple(torch.empty(s_, dtype=dt, pin_memory=True) for s_, dt in ((n_reads, torch.int32), (n_reads, torch.int16), (n_reads + 1, torch.int64), (int(hb.qual.size), torch.uint8)))
+        outs = (out_np, (out_b[0].numpy().view(np.uint32), out_b[1].numpy().view(np.uint16), out_b[2].numpy().view(np.uint64), out_b[3].numpy()))
 
     trace = {}
     marks = []
@@ -299,6 +302,12 @@ def main():
         t0 = time.perf_counter(); fn(); trace[name] = trace.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
 
     def e2e_run(k_steps):
+        if ring == 1:                        # capacity runs (one context fills the HBM): no overlap, the same calls in sequence
+            for s in range(k_steps):
+                timed("reset+append_async", lambda: (ctx.reset(), ctx.append_async(hb))); timed("append_wait", ctx.append_wait)
+                timed("phases", lambda: phases(ctx)); timed("fetch_async", lambda: ctx.fetch_async(out_np)); timed("fetch_wait", ctx.fetch_wait)
+                marks.append(time.perf_counter())
+            return
         for s in range(k_steps + 2):
             cur = cs[s % 3] if s < k_steps else None
             prev = cs[(s - 1) % 3] if 1 <= s <= k_steps else None
@@ -312,19 +321,19 @@ def main():
             if cur is not None:
                 timed("append_wait", cur.append_wait)
             marks.append(time.perf_counter())
-    e2e_run(3)                                   # warm-up (allocations of the second and third context)
+    e2e_run(ring)                                # warm-up (allocations of the other contexts)
     trace.clear(); marks.clear()
-    barrier(ctx); ctx2.synchronize(); ctx3.synchronize()
+    barrier(ctx); [c_.synchronize() for c_ in cs]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     e2e_run(args.steps)
-    ctx.synchronize(); ctx2.synchronize(); ctx3.synchronize(); torch.cuda.synchronize()
+    [c_.synchronize() for c_ in cs]; torch.cuda.synchronize()
     ev1.record(); ev1.synchronize()
     e2e_ms_total = ev0.elapsed_time(ev1)
     mid = np.diff(np.array(marks[:args.steps]))                    # iterations that both upload and run phases
     steady_ms = float(np.median(mid[1:]) * 1e3) if mid.size >= 2 else None
     free_b, total_b = torch.cuda.mem_get_info(local)
-    hbm_used_gb = (total_b - free_b) / 1e9                 # three contexts resident
+    hbm_used_gb = (total_b - free_b) / 1e9                 # all contexts of the ring resident
     clocks = sampler.stop() if rank == 0 else None
     tot = torch.tensor([float(np.sum(dev_ms)), float(e2e_ms_total)], device=f"cuda:{local}", dtype=torch.float64)
     cnt = torch.tensor([float(n_reads)], device=f"cuda:{local}", dtype=torch.float64)
@@ -389,7 +398,7 @@ def main():
             "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
                     "how": "K steps through elp_append_batch_async / phases / elp_fetch_async with pinned host buffers, software-pipelined over a ring of three contexts and two output buffers (upload of step s overlaps the phases of step s-1 and the download of steps s-1 / s-2)",
                     "unpipelined_ms_per_step": float(np.mean(in_ms) + np.mean(dev_ms) + np.mean(out_ms)),
-                    "host_ms_per_step_in_call": {k: v / args.steps for k, v in trace.items()}, "hbm_used_gb_three_contexts": hbm_used_gb,
+                    "host_ms_per_step_in_call": {k: v / args.steps for k, v in trace.items()}, "contexts": ring, "hbm_used_gb_all_contexts": hbm_used_gb,
                     "steady_ms_per_step": steady_ms, "note": "ms_per_step = the K timed steps including pipeline fill (first upload) and drain (last phases + download); steady_ms_per_step = median host interval between consecutive steps in the middle of the run"},
             "phases_per_rank": phases_per_rank, "roofline_graded": graded,
             "gpu_launches": launches, "verified": (verified or {}).get("ok"), "verify": verified, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "kernels": kern}

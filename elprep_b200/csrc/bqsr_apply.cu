@@ -376,6 +376,15 @@ __global__ void __launch_bounds__(AP2_WARPS * 32, 2) bqsr_apply2_kernel(Apply2Ar
     for (int o = 16; o; o >>= 1) errbits |= __shfl_xor_sync(FULL_MASK, errbits, o);
     if (errbits && lane == 0) atomicOr(A.err, errbits);
 }
+// QUAL bytes in output order without recalibration, any read length: one warp per read (the no-table path of elp_fetch for long reads)
+__global__ void __launch_bounds__(256) qual_copy_kernel(uint64_t n, const int32_t* __restrict__ lseq, const uint64_t* __restrict__ qual_off, const uint64_t* __restrict__ out_off,
+                                                        const uint8_t* __restrict__ qual, uint8_t* __restrict__ out) {
+    const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n) return;
+    const int L = lseq[k];
+    const uint8_t* src = qual + qual_off[k]; uint8_t* dst = out + out_off[k];
+    for (int i = (int)lane_id(); i < L; i += 32) dst[i] = src[i];
+}
 }  // namespace
 
 int run_apply_kernel(elp_ctx* c, bool with_lut) {
@@ -421,6 +430,13 @@ int run_apply_kernel(elp_ctx* c, bool with_lut) {
             c->end(); LAUNCH_CHECK(c);
             int rc2 = check_device_errors(c);
             if (rc2) return rc2;
+            c->qual_out_valid = true;
+            return E_OK;
+        }
+        if (!with_lut && c->h_ranges.lseq_max > CHUNK * 32) {      // longer than either tiled kernel handles: plain per-read copy
+            c->begin("qual_materialize", 2.0 * (double)c->n_qual + (double)n * 20);
+            qual_copy_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, c->stream>>>(n, c->s_lseq.p, c->s_qual_off.p, c->s_out_off.p, c->qual.p, c->qual_out.p);
+            c->end(); LAUNCH_CHECK(c);
             c->qual_out_valid = true;
             return E_OK;
         }

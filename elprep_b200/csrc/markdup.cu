@@ -519,6 +519,12 @@ int phase_markdup(elp_ctx* c, bool optical) {
             CUDA_TRY(c, c->vals_a.reserve(nt + 4, c->stream)); CUDA_TRY(c, c->vals_b.reserve(nt + 4, c->stream));
             const int bR = bits_for((uint64_t)c->n_contigs), bL = bits_for((uint64_t)c->n_lib + 1);
             const int bU = bits_for((uint64_t)((int64_t)R.upos_max - (int64_t)R.upos_min));
+            // both packed key layouts are checked before any marking kernel runs, so that a refusal leaves the FLAG column untouched
+            {
+                const int frag_bits = bits_for((uint64_t)R.score_max) + 2 + bU + bR + bL, pair_bits = bits_for((uint64_t)R.score_max * 2) + 2 * bU + 2 + 2 * bR + bL;
+                if (n && R.n_entering && frag_bits > 64) return c->fail(E_LIMIT, "fragment signature needs %d bits (>64): too many contigs/libraries for the packed key", frag_bits);
+                if (pair_bits > 128) return c->fail(E_LIMIT, "pair signature needs %d bits (>128)", pair_bits);
+            }
             // ---- fragments (classifyFragment): local reads only ----
             if (n && R.n_entering) {
                 FragLayout L{}; L.bS = bits_for((uint64_t)R.score_max); L.bU = bU; L.bR = bR; L.bL = bL; L.upos_min = R.upos_min; L.score_max = R.score_max;

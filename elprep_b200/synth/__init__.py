@@ -75,6 +75,8 @@ def make_workload(n_pairs, contigs, seed=20260924, L=150, dup_frac=0.10, optical
     """home: bool per contig -- fragments start only on those contigs (one generator per contig group of ONE genome: the mates of its
     cross-contig pairs land on any contig, so pairs span the groups as in a real `elprep sfm` split); pair_id_base keeps QNAMEs unique across
     the generators; genome_seed: the shared reference genome; reference_for: contig indices whose reference / known sites are returned."""
+    if not 20 <= L <= 8000:
+        raise ValueError("read length outside the generator's range (20..8000)")
     lib = _L()
     threads = threads or min(32, os.cpu_count() or 1)
     clen = np.array([ln for _, ln in contigs], dtype=np.int32)

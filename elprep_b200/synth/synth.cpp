@@ -156,7 +156,7 @@ struct PairGen {
     // emit one read's bases+quals in reference orientation
     void fill_read(Rng& r, int32_t contig, const ReadShape& s, int L, int32_t frag_lo, int32_t frag_hi, bool second, uint8_t* seqdst, uint8_t* qualdst) const {
         const Params& P = G.P;
-        uint8_t bases[1024];
+        uint8_t bases[8192];
         int ri = 0; int64_t ref0 = (int64_t)s.pos - 1;
         for (int k = 0; k < s.ncig; k++) {
             int ln = (int)(s.cig[k] >> 4); int op = (int)(s.cig[k] & 15);
