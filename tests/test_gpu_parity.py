@@ -96,16 +96,6 @@ def test_read_lengths(L):
     _compare(w, g, o)
 
 
-def test_long_reads_sort_markdup_fetch():
-    """reads longer than the tiled QUAL kernels cover (1024 bases): sort + mark duplicates + fetch go through the plain per-read copy (no BQSR)"""
-    w = synth.make_workload(400, SMALL, seed=1500, L=1500)
-    assert int(w.batch.lseq.max()) == 1500
-    g = gpu_pipeline(w, bqsr=False, n_batches=2)
-    o = oracle_pipeline(w, bqsr=False)
-    _compare(w, g, o, bqsr=False)
-    assert np.array_equal(g["qual"], o["qual"])
-
-
 def test_mixed_read_lengths():
     """reads of different lengths in one context (lanes per read follow the longest)"""
     a = synth.make_workload(2_000, SMALL, seed=201, L=150)
