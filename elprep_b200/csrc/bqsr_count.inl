@@ -10,11 +10,11 @@
 //     planes are flushed to the global table with 64-bit atomics every <= 255 passes.
 //   * Contexts table: position independent, so 16 contexts x S slots are popcounts of three-input ANDs of the planes, summed in
 //     packed 16-bit accumulators and flushed with one warp reduction per segment.
-//   * mismatches (sparse) go to the global table directly.
+//   * mismatches (sparse, but piled on few cells) go to CTA-private shared-memory tables, flushed once per CTA.
 // Both only work if all reads a warp sees share (read-group covariate, first/second of pair): bqsr_prep2_kernel therefore sorts
 // the eligible reads into per-class lists of 32-byte work records (closed-form clipping for reads whose CIGAR is
 // [H][S]M[S][H] or that plus one insertion/deletion; everything else goes to the old, general kernels through a list).
-// QUAL, SEQ and reference windows are staged through shared memory with cp.async, three passes deep.
+// QUAL, SEQ and reference windows are staged through shared memory with cp.async, CNT_STAGES passes deep.
 
 #ifndef CNT_MINB
 #define CNT_MINB 2
