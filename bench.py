@@ -212,7 +212,8 @@ def main():
         home = np.array([1 if owner[i] == rank else 0 for i in range(len(all_contigs))], np.uint8)
         w = synth.make_workload(args.reads // 2, all_contigs, seed=20260924 + rank, home=home, pair_id_base=rank * 10**10, genome_seed=20260924,
                                 reference_for=my_contigs, threads=max(4, threads // max(1, world)))
-        batch = multi.redistribute(w.batch, owner, rank, world, multi.torch_gather_objects())
+        gen_threads = max(4, threads // max(1, world))
+        batch = multi.redistribute(w.batch, owner, rank, world, multi.torch_gather_objects(), take=lambda b, idx: synth.take(b, idx, threads=gen_threads))
         w.batch = batch
     log(f"[rank {rank}] {batch.n} reads on {len(my_contigs)} of {len(all_contigs)} contigs, generated in {time.time() - t0:.1f}s")
     hb = pinned(batch)

@@ -169,10 +169,11 @@ def merge_spread_metrics(ctx, spread_metrics):
         ctx.optical_merge(slot, counters, m["hist"])
 
 
-def redistribute(batch, owner, rank, world, gather_objects):
+def redistribute(batch, owner, rank, world, gather_objects, take=None):
     """The `split` step of an sfm run for one rank's share of the input (sam/split-merge.go:178-311): reads whose contig belongs to another
     rank are handed to that rank, reads arriving from the others are appended.  Unmapped reads (REFID -1) stay where they are.  Host-side
     setup (numpy + one object all-gather), not part of any timed region: the device library starts from reads that are already home."""
+    take = take or (lambda b, idx: b.take(idx))      # (bench.py passes synth.take: host threads instead of element-wise numpy index arrays)
     refid = batch.refid
     dest = np.where(refid >= 0, owner[np.maximum(refid, 0)], rank)
     out = {}
@@ -180,9 +181,9 @@ def redistribute(batch, owner, rank, world, gather_objects):
         if dst != rank:
             sel = np.nonzero(dest == dst)[0]
             if sel.size:
-                out[dst] = _pack(batch.take(sel))
+                out[dst] = _pack(take(batch, sel))
     inbox = gather_objects(out)
-    parts = [batch.take(np.nonzero(dest == rank)[0])]
+    parts = [take(batch, np.nonzero(dest == rank)[0])]
     for src in range(world):
         if src != rank and rank in inbox[src]:
             parts.append(_unpack(inbox[src][rank]))

@@ -155,3 +155,37 @@ def test_two_rank_spread_pairs(tmp_path, world):
                 assert tot[k] == exp[k], (slot, k)
         assert hist == wm.hist[slot], slot
     assert spread_dups > 10
+
+
+def _split_worker(rank, world, port, out_dir):
+    """the input side of `bench.py --gpus 2`: one genome, each rank generates the pairs that start in its contig group, then the split step"""
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import bench
+    from elprep_b200 import multi, synth
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    contigs = [("c1", 300_000), ("c2", 250_000), ("c3", 120_000), ("c4", 80_000)]
+    groups = bench.contig_groups(contigs, world)
+    header = synth.make_header(contigs)
+    owner = multi.owner_table(header, groups)
+    home = np.array([1 if owner[i] == rank else 0 for i in range(len(contigs))], np.uint8)
+    w = synth.make_workload(5000, contigs, seed=900 + rank, home=home, pair_id_base=rank * 10**9, genome_seed=5, cross_contig_frac=0.05, threads=2, want_reference=False)
+    a = multi.redistribute(w.batch, owner, rank, world, multi.torch_gather_objects())
+    b = multi.redistribute(w.batch, owner, rank, world, multi.torch_gather_objects(), take=lambda x, idx: synth.take(x, idx, threads=2))
+    same = all(np.array_equal(getattr(a, f), getattr(b, f)) for f in a.FIELDS)
+    at_home = bool(np.all(np.where(a.refid >= 0, owner[np.maximum(a.refid, 0)], rank) == rank))
+    cross = int(((a.refid >= 0) & (a.nref >= 0) & (owner[np.maximum(a.refid, 0)] != owner[np.maximum(a.nref, 0)])).sum())
+    np.save(os.path.join(out_dir, f"split_{rank}.npy"), np.array([int(same), int(at_home), cross, a.n, w.batch.n]))
+    dist.barrier(); dist.destroy_process_group()
+
+
+def test_two_rank_split_of_one_genome(tmp_path):
+    """after the split step every read sits on the rank that owns its contig, no read is lost, pairs still span the ranks, and the threaded
+    gather bench.py uses gives the same batch as the numpy one"""
+    import torch.multiprocessing as mp
+    port = 29300 + (os.getpid() % 300)
+    mp.spawn(_split_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r = [np.load(os.path.join(str(tmp_path), f"split_{k}.npy")) for k in range(2)]
+    assert all(x[0] == 1 and x[1] == 1 and x[2] > 0 for x in r)
+    assert r[0][3] + r[1][3] == r[0][4] + r[1][4]
