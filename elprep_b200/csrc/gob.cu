@@ -110,8 +110,9 @@ struct Dec {
         }
         types[id] = t;
     }
-    ValP value(int id) {
+    ValP value(int id, int depth = 0) {
         auto v = std::make_shared<Val>();
+        if (depth > 32) bad = true;          // (a crafted self-referential type must not recurse through the whole file)
         if (bad) return v;
         switch (id) {
             case 1: v->kind = 1; v->u = u(); return v;                 // bool
@@ -126,13 +127,13 @@ struct Dec {
         const TypeDef& t = it->second;
         if (t.kind == 3) {
             v->kind = 3; int f = -1;
-            for (;;) { uint64_t d = u(); if (bad || !d) break; f += (int)d; if (f < 0 || f >= (int)t.fields.size()) { bad = true; break; } v->fields[t.fields[f].first] = value(t.fields[f].second); }
+            for (;;) { uint64_t d = u(); if (bad || !d) break; if (d > (1u << 20)) { bad = true; break; } f += (int)d; if (f < 0 || f >= (int)t.fields.size()) { bad = true; break; } v->fields[t.fields[f].first] = value(t.fields[f].second, depth + 1); }
         } else if (t.kind == 4) {
             v->kind = 4; uint64_t n = u();
-            for (uint64_t k = 0; k < n && !bad; k++) { ValP a = value(t.key); ValP b = value(t.elem); v->kv.push_back({a, b}); }
+            for (uint64_t k = 0; k < n && !bad; k++) { ValP a = value(t.key, depth + 1); ValP b = value(t.elem, depth + 1); v->kv.push_back({a, b}); }
         } else if (t.kind == 5 || t.kind == 7) {
             v->kind = 5; uint64_t n = u();
-            for (uint64_t k = 0; k < n && !bad; k++) v->items.push_back(value(t.elem));
+            for (uint64_t k = 0; k < n && !bad; k++) v->items.push_back(value(t.elem, depth + 1));
         } else bad = true;
         return v;
     }
