@@ -217,6 +217,7 @@ def main():
         w.batch = batch
     log(f"[rank {rank}] {batch.n} reads on {len(my_contigs)} of {len(all_contigs)} contigs, generated in {time.time() - t0:.1f}s")
     hb = pinned(batch)
+    w.batch = batch = hb           # one host copy of the reads from here on (the page-locked one): the CPU legs and --verify read the same arrays
     n_reads = hb.n
     h2d = sum(getattr(hb, f).nbytes for f in hb.FIELDS)
 
