@@ -398,7 +398,8 @@ def main():
             "ms_per_step": dev_total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int64", "data": "synthetic",
             "config": {"workload": workload_name, "cpu_arm": f"CPU arm runs a sample: the first {args.cpu_sample} reads per step", "reads_per_gpu": n_reads, "parallelism": f"contig-group x{world}; NCCL inside the C ABI: spread-pair exchange (ncclSend/Recv) in elp_sort_markdup + one ncclAllReduce of the BQSR tables", "flush": "inputs >> L2 (re-ingested every step)"},
             "e2e": {"value": e2e, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_total_ms / args.steps,
-                    "how": "K steps through elp_append_batch_async / phases / elp_fetch_async with pinned host buffers, software-pipelined over a ring of three contexts and two output buffers (upload of step s overlaps the phases of step s-1 and the download of steps s-1 / s-2)",
+                    "how": ("K steps through elp_append_batch_async / phases / elp_fetch_async with pinned host buffers, " +
+                            ("software-pipelined over a ring of three contexts and two output buffers (upload of step s overlaps the phases of step s-1 and the download of steps s-1 / s-2)" if ring > 1 else "one context, the calls in sequence (no overlap)")),
                     "unpipelined_ms_per_step": float(np.mean(in_ms) + np.mean(dev_ms) + np.mean(out_ms)),
                     "host_ms_per_step_in_call": {k: v / args.steps for k, v in trace.items()}, "contexts": ring, "hbm_used_gb_all_contexts": hbm_used_gb,
                     "steady_ms_per_step": steady_ms, "note": "ms_per_step = the K timed steps including pipeline fill (first upload) and drain (last phases + download); steady_ms_per_step = median host interval between consecutive steps in the middle of the run"},
